@@ -1,0 +1,78 @@
+"""ctypes binding of libgkd.so (include/gkd.h).  Fails loudly when the CUDA library is missing:
+there is no CPU fallback anywhere in this package."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libgkd.so")
+
+GKD_OK, GKD_EINVAL, GKD_EIO, GKD_ENOMEM, GKD_ECUDA, GKD_ESTATE = 0, -1, -2, -3, -4, -5
+DNA, PROT, RNA = 0, 1, 2
+STRAND_BOTH, STRAND_CANONICAL = 0, 1
+
+
+class GkdConfig(C.Structure):
+    _fields_ = [("device", C.c_int32), ("k", C.c_int32), ("alphabet", C.c_int32), ("strand_mode", C.c_int32),
+                ("workspace_bytes", C.c_uint64), ("segment_keys", C.c_uint32), ("reserved", C.c_uint32 * 7)]
+
+
+class GkdMetrics(C.Structure):
+    _fields_ = [("pack_ms", C.c_double), ("encode_ms", C.c_double), ("sort_ms", C.c_double), ("unique_ms", C.c_double),
+                ("intersect_ms", C.c_double), ("epilogue_ms", C.c_double), ("h2d_ms", C.c_double), ("d2h_ms", C.c_double),
+                ("residues_packed", C.c_uint64), ("kmer_positions", C.c_uint64), ("keys_sorted", C.c_uint64),
+                ("sort_passes", C.c_uint32), ("reserved0", C.c_uint32), ("keys_unique", C.c_uint64), ("pairs", C.c_uint64),
+                ("intersect_bytes", C.c_uint64), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64),
+                ("launches", C.c_uint64), ("intersect_launches", C.c_uint64), ("reserved", C.c_uint64 * 6)]
+
+
+# every symbol include/gkd.h declares: name -> (restype, argtypes)
+_vp, _u32, _u64, _i32, _dbl = C.c_void_p, C.c_uint32, C.c_uint64, C.c_int, C.c_double
+_pu32, _pu64, _pdbl = C.POINTER(C.c_uint32), C.POINTER(C.c_uint64), C.POINTER(C.c_double)
+SYMBOLS = {
+    "gkd_abi_version": (_i32, []),
+    "gkd_create": (_i32, [C.POINTER(_vp), C.POINTER(GkdConfig)]),
+    "gkd_destroy": (_i32, [_vp]),
+    "gkd_reset": (_i32, [_vp]),
+    "gkd_last_error": (C.c_char_p, [_vp]),
+    "gkd_add_sequences": (_i32, [_vp, C.POINTER(_vp), _pu64, _u32, _pu32]),
+    "gkd_add_fasta_file": (_i32, [_vp, C.c_char_p, _i32, _pu32, _pu32]),
+    "gkd_label": (C.c_char_p, [_vp, _u32]),
+    "gkd_comment": (C.c_char_p, [_vp, _u32]),
+    "gkd_count": (_u32, [_vp]),
+    "gkd_build_sets": (_i32, [_vp]),
+    "gkd_set_size": (_i32, [_vp, _u32, _pu64, _pu64, _pu64]),
+    "gkd_export_set": (_i32, [_vp, _u32, _vp, _u64, _pu64]),
+    "gkd_set_device_ptr": (_i32, [_vp, _u32, C.POINTER(_vp), _pu64]),
+    "gkd_import_set": (_i32, [_vp, _vp, _u64, _pu32]),
+    "gkd_all_vs_all": (_i32, [_vp, _vp, _vp]),
+    "gkd_all_vs_all_range": (_i32, [_vp, _u32, _u64, _u64, _vp, _vp]),
+    "gkd_query_vs_ref": (_i32, [_vp, _vp, _u32, _vp, _u32, _vp, _vp]),
+    "gkd_pairs": (_i32, [_vp, _vp, _vp, _u64, _vp, _vp]),
+    "gkd_pair": (_i32, [_vp, _u32, _u32, _pu64, _pu64, _pdbl]),
+    "gkd_format_double": (_i32, [_dbl, C.c_char_p, C.c_size_t]),
+    "gkd_get_metrics": (_i32, [_vp, C.POINTER(GkdMetrics)]),
+    "gkd_stream": (_vp, [_vp]),
+    "gkd_synth_dna": (_i32, [_i32, _vp, _u64, _u64, _u32, _u32, _dbl]),
+    "gkd_synth_protein": (_i32, [_i32, _vp, _u64, _u64, _u32, _u32, _dbl]),
+}
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """dlopen libgkd.so and type every entry point.  Raises if the library or a symbol is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                          "(genome.distance_b200 has no CPU fallback)")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SYMBOLS.items():
+        fn = getattr(lib, name)  # AttributeError if the symbol is not exported
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib

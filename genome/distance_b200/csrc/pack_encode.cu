@@ -1,0 +1,225 @@
+// pack_encode.cu -- kernel 1 (residue text -> packed codes + invalid mask) and kernel 2 (rolling
+// canonical k-mer encoding) of libgkd.so.  sm_100a only.
+//
+// Reference semantics restated:
+//   DnaKmers / GenomeKmers: lower-case the sequence, take every K-substring of it and of its reverse
+//   complement (KmerType.DNA.createKmers, FastaDistanceProcessor.java:153,184; GenomeProcessor.java:109).
+//   Here both strands are represented by ONE canonical key min(fwd, revcomp) per position; the
+//   both-strand set sizes are recovered exactly as 2|C| - P (palindromes P counted in kernel 3).
+//   ProteinKmers: every K-substring, single strand (ProteinKmerReader.java:100-101); key = the K raw
+//   bytes, first character most significant, so key order is String order.
+// Bound: HBM.  Algorithmic bytes: kernel 1 = 1 B read + 0.375 B written per residue (2-bit code +
+// 1-bit mask); kernel 2 = 0.375 B read + 8 B written per k-mer position.
+#include "gkd_internal.cuh"
+
+namespace gkd {
+
+// ------------------------------------------------------------------------------------------------
+// kernel 1: pack
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t nonzero_bytes(uint32_t v) {
+    // bit 7 of each byte set iff that byte of v is non-zero
+    return (((v & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | v) & 0x80808080u;
+}
+
+// one thread = 32 residues = one uint64 of codes + one uint32 of mask
+__global__ void __launch_bounds__(256) k_pack_dna(const char *__restrict__ text, uint64_t n_pos, uint64_t n_words,
+                                                   uint64_t *__restrict__ codes, uint32_t *__restrict__ mask, int rna) {
+    uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= n_words) return;
+    uint64_t p0 = w * PACK_POS_PER_WORD;
+    uint32_t x[8];
+    const char *src = text + p0;
+    if (p0 + 32 <= n_pos && ((reinterpret_cast<uintptr_t>(src) & 15) == 0)) {
+        uint4 a = __ldg(reinterpret_cast<const uint4 *>(src));
+        uint4 b = __ldg(reinterpret_cast<const uint4 *>(src) + 1);
+        x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w;
+        x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
+    } else {
+#pragma unroll
+        for (int q = 0; q < 8; q++) {
+            uint32_t v = 0;
+#pragma unroll
+            for (int e = 0; e < 4; e++) {
+                uint64_t p = p0 + q * 4 + e;
+                uint32_t c = (p < n_pos) ? (uint8_t)text[p] : 0u;
+                v |= c << (8 * e);
+            }
+            x[q] = v;
+        }
+    }
+    uint64_t code = 0;
+    uint32_t inval = 0;
+#pragma unroll
+    for (int q = 0; q < 8; q++) {
+        uint32_t v = x[q];
+        uint32_t lower = v | 0x20202020u;  // String.toLowerCase for letters
+        if (rna) {                         // u reads as t
+            uint32_t is_u = ~nonzero_bytes(lower ^ 0x75757575u) & 0x80808080u;
+            lower &= ~(is_u >> 7);
+        }
+        // a=0 c=1 g=2 t=3 from bits 1..3 of the character
+        uint32_t t = ((v >> 1) ^ (v >> 2)) & 0x03030303u;
+        // the character each code stands for; a mismatch marks the position invalid
+        uint32_t sel = (t & 0x3u) | ((t >> 4) & 0x30u) | ((t >> 8) & 0x300u) | ((t >> 12) & 0x3000u);
+        uint32_t expect = __byte_perm(0x74676361u, 0u, sel);
+        uint32_t bad = nonzero_bytes(expect ^ lower);
+        uint32_t c8 = ((t * 0x00041041u) >> 18) & 0xFFu;                            // 4 codes -> 8 bits
+        uint32_t m4 = ((((bad >> 7) & 0x01010101u) * 0x00204081u) >> 21) & 0xFu;    // 4 flags -> 4 bits
+        code |= (uint64_t)c8 << (8 * q);
+        inval |= m4 << (4 * q);
+    }
+    // invalid positions carry code 0 so the stream is deterministic
+    codes[w] = code;
+    mask[w] = inval;
+}
+
+__global__ void __launch_bounds__(256) k_pack_prot(const char *__restrict__ text, uint64_t n_pos, uint64_t n_words,
+                                                    uint8_t *__restrict__ codes, uint32_t *__restrict__ mask) {
+    uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= n_words) return;
+    uint64_t p0 = w * PACK_POS_PER_WORD;
+    uint32_t inval = 0;
+    uint32_t x[8];
+#pragma unroll
+    for (int q = 0; q < 8; q++) {
+        uint32_t v = 0;
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+            uint64_t p = p0 + q * 4 + e;
+            uint32_t c = (p < n_pos) ? (uint8_t)text[p] : 0u;
+            v |= c << (8 * e);
+            if (c == (uint8_t)STREAM_SEPARATOR) inval |= 1u << (q * 4 + e);
+        }
+        x[q] = v;
+    }
+    uint4 *dst = reinterpret_cast<uint4 *>(codes + p0);  // code buffer is 32-byte aligned and padded
+    dst[0] = make_uint4(x[0], x[1], x[2], x[3]);
+    dst[1] = make_uint4(x[4], x[5], x[6], x[7]);
+    mask[w] = inval;
+}
+
+cudaError_t launch_pack_dna(const char *text, uint64_t n_pos, uint64_t *codes, uint32_t *mask, int rna,
+                            cudaStream_t s) {
+    // one extra all-invalid word so kernel 2 may read word w+1 unconditionally
+    uint64_t n_words = (n_pos + PACK_POS_PER_WORD - 1) / PACK_POS_PER_WORD + 1;
+    uint64_t blocks = (n_words + 255) / 256;
+    k_pack_dna<<<(unsigned)blocks, 256, 0, s>>>(text, n_pos, n_words, codes, mask, rna);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_pack_prot(const char *text, uint64_t n_pos, uint8_t *codes, uint32_t *mask, cudaStream_t s) {
+    uint64_t n_words = (n_pos + PACK_POS_PER_WORD - 1) / PACK_POS_PER_WORD + 1;
+    uint64_t blocks = (n_words + 255) / 256;
+    k_pack_prot<<<(unsigned)blocks, 256, 0, s>>>(text, n_pos, n_words, codes, mask);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// kernel 2: rolling canonical encode
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t reverse_pairs(uint64_t x) {
+    uint64_t y = __brevll(x);
+    return ((y >> 1) & 0x5555555555555555ull) | ((y & 0x5555555555555555ull) << 1);
+}
+
+// which genome of the batch owns tile `tile` (tile_first is ascending)
+__device__ __forceinline__ uint32_t find_genome(const BatchGenome *__restrict__ g, uint32_t n, uint32_t tile) {
+    uint32_t lo = 0, hi = n;
+    while (hi - lo > 1) {
+        uint32_t mid = (lo + hi) >> 1;
+        if (g[mid].tile_first <= tile) lo = mid;
+        else hi = mid;
+    }
+    return lo;
+}
+
+constexpr int ENC_STRIDE = ENC_PER_THREAD + 1;  // smem padding: conflict-free 64-bit stores
+
+template <int ALPHA>
+__global__ void __launch_bounds__(ENC_THREADS)
+    k_encode(const BatchGenome *__restrict__ genomes, uint32_t n_genomes, int k, uint64_t *__restrict__ keys_out) {
+    __shared__ uint64_t stage[ENC_THREADS * ENC_STRIDE];
+    __shared__ uint32_t s_g;
+    if (threadIdx.x == 0) s_g = find_genome(genomes, n_genomes, blockIdx.x);
+    __syncthreads();
+    const BatchGenome G = genomes[s_g];
+    const uint32_t tile = blockIdx.x - G.tile_first;
+    const uint32_t slot0 = tile * ENC_TILE;                    // first slot of this tile
+    const uint32_t my0 = slot0 + threadIdx.x * ENC_PER_THREAD;  // first slot of this thread
+    uint64_t *mine = stage + threadIdx.x * ENC_STRIDE;
+
+    if (my0 < G.n_slots) {
+        const uint32_t w0 = my0 / PACK_POS_PER_WORD;
+        const uint32_t off = my0 % PACK_POS_PER_WORD;  // 0 or 16
+        // invalid bits for relative positions 0..47
+        uint64_t inv = (((uint64_t)__ldg(G.mask + w0 + 1) << 32) | __ldg(G.mask + w0)) >> off;
+        const uint64_t kbits = (k >= 64) ? ~0ull : ((1ull << k) - 1);
+        if (ALPHA == GKD_PROT) {
+            const uint64_t kmask = (k >= 8) ? ~0ull : ((1ull << (8 * k)) - 1);
+            const uint8_t *bytes = reinterpret_cast<const uint8_t *>(G.codes) + my0;
+            // 16 slots need bytes [0, 16 + k - 1) <= 23: three aligned 8-byte loads
+            const uint64_t *q = reinterpret_cast<const uint64_t *>(bytes);
+            uint64_t b0 = __ldg(q), b1 = __ldg(q + 1), b2 = __ldg(q + 2);
+            uint64_t key = 0;
+#pragma unroll
+            for (int r = 0; r < ENC_PER_THREAD + 7; r++) {
+                uint64_t word = r < 8 ? b0 : (r < 16 ? b1 : b2);
+                uint32_t c = (uint32_t)(word >> (8 * (r & 7))) & 0xFFu;
+                key = ((key << 8) | c) & kmask;
+                int j = r - (k - 1);  // slot completed by this byte
+                if (j >= 0 && j < ENC_PER_THREAD) {
+                    bool ok = ((inv >> j) & kbits) == 0 && (my0 + j) < G.n_slots;
+                    mine[j] = ok ? key : KEY_SENTINEL;
+                }
+            }
+        } else {
+            const uint64_t kmask = (k >= 32) ? ~0ull : ((1ull << (2 * k)) - 1);
+            const int top = 2 * (k - 1);
+            const uint64_t *cw = G.codes + w0;
+            uint64_t c0 = __ldg(cw), c1 = __ldg(cw + 1);
+            uint64_t lo, hi;  // 128-bit little-endian window starting at this thread's first base
+            if (off) {
+                lo = (c0 >> (2 * off)) | (c1 << (64 - 2 * off));
+                hi = c1 >> (2 * off);
+            } else {
+                lo = c0;
+                hi = c1;
+            }
+            // v = the K bases as stored (first base least significant): as a number that is the
+            // REVERSED k-mer, so the reverse-complement key is simply its complement.
+            uint64_t v = lo & kmask;
+            uint64_t fwd = reverse_pairs(v) >> (64 - 2 * k);
+#pragma unroll
+            for (int j = 0; j < ENC_PER_THREAD; j++) {
+                uint64_t rc = (~v) & kmask;
+                uint64_t key = fwd < rc ? fwd : rc;
+                bool ok = ((inv >> j) & kbits) == 0 && (my0 + j) < G.n_slots;
+                mine[j] = ok ? key : KEY_SENTINEL;
+                // slide one base: the 128-bit window shifts right by one code
+                lo = (lo >> 2) | (hi << 62);
+                hi >>= 2;
+                v = lo & kmask;
+                fwd = ((fwd << 2) | ((v >> top) & 3ull)) & kmask;
+            }
+        }
+    }
+    __syncthreads();
+    // coalesced write-out of the tile
+    const uint32_t remaining = G.n_slots > slot0 ? G.n_slots - slot0 : 0;
+    const uint32_t count = remaining < (uint32_t)ENC_TILE ? remaining : (uint32_t)ENC_TILE;
+    uint64_t *dst = keys_out + G.raw_off + slot0;
+#pragma unroll 4
+    for (uint32_t idx = threadIdx.x; idx < count; idx += ENC_THREADS)
+        dst[idx] = stage[(idx / ENC_PER_THREAD) * ENC_STRIDE + (idx % ENC_PER_THREAD)];
+}
+
+cudaError_t launch_encode(const BatchGenome *genomes, uint32_t n_genomes, uint32_t n_tiles, int alphabet, int k,
+                          uint64_t *keys_out, cudaStream_t s) {
+    if (n_tiles == 0) return cudaSuccess;
+    if (alphabet == GKD_PROT) k_encode<GKD_PROT><<<n_tiles, ENC_THREADS, 0, s>>>(genomes, n_genomes, k, keys_out);
+    else k_encode<GKD_DNA><<<n_tiles, ENC_THREADS, 0, s>>>(genomes, n_genomes, k, keys_out);
+    return cudaGetLastError();
+}
+
+}  // namespace gkd

@@ -1,0 +1,334 @@
+// sort_unique.cu -- kernel 3 of libgkd.so: hand-written segmented LSD radix sort of every genome's
+// k-mer keys followed by a unique/compaction pass that emits the sorted canonical key set plus the
+// sorted list of its reverse-palindromic members.  sm_100a only; no CUB/Thrust.
+//
+// Reference semantics restated: HashSet<String>.add ignores duplicates, so a genome's set is the
+// DISTINCT k-mers (KmerCountProcessor.java:76-77 iterates the set; SequenceKmers.distance works on
+// set sizes, FastaDistanceProcessor.java:186).  Sorting + adjacent-unique gives the same set exactly.
+//
+// Bound: HBM.  Ideal algorithmic bytes are 16 B/key (read once, write once); this LSD implementation
+// physically moves 24 B/key per pass (8 B histogram read + 8 B read + 8 B write) over
+// ceil(key_bits / 8) passes, plus 8 B (count) + 16 B (compact write) for the unique pass.
+#include "gkd_internal.cuh"
+
+namespace gkd {
+
+__device__ __forceinline__ uint32_t find_genome_s(const BatchGenome *__restrict__ g, uint32_t n, uint32_t tile) {
+    uint32_t lo = 0, hi = n;
+    while (hi - lo > 1) {
+        uint32_t mid = (lo + hi) >> 1;
+        if (g[mid].tile_first <= tile) lo = mid;
+        else hi = mid;
+    }
+    return lo;
+}
+
+constexpr int SORT_WARPS = SORT_THREADS / 32;
+
+// ---- per-tile digit histogram -------------------------------------------------------------------
+__global__ void __launch_bounds__(SORT_THREADS)
+    k_radix_hist(const BatchGenome *__restrict__ genomes, uint32_t n_genomes, const uint64_t *__restrict__ keys,
+                 uint32_t *__restrict__ tile_hist, int shift, uint32_t dmask) {
+    __shared__ uint32_t s_hist[SORT_WARPS][RADIX_BINS];
+    __shared__ uint32_t s_g;
+    if (threadIdx.x == 0) s_g = find_genome_s(genomes, n_genomes, blockIdx.x);
+    for (int i = threadIdx.x; i < SORT_WARPS * RADIX_BINS; i += SORT_THREADS) (&s_hist[0][0])[i] = 0;
+    __syncthreads();
+    const BatchGenome G = genomes[s_g];
+    const uint32_t slot0 = (blockIdx.x - G.tile_first) * SORT_TILE;
+    const uint32_t count = min((uint32_t)SORT_TILE, G.n_slots - slot0);
+    const uint64_t *src = keys + G.raw_off + slot0;
+    const int warp = threadIdx.x >> 5;
+#pragma unroll 4
+    for (uint32_t idx = threadIdx.x; idx < count; idx += SORT_THREADS) {
+        uint32_t d = (uint32_t)(src[idx] >> shift) & dmask;
+        atomicAdd(&s_hist[warp][d], 1u);
+    }
+    __syncthreads();
+    for (int d = threadIdx.x; d < RADIX_BINS; d += SORT_THREADS) {
+        uint32_t c = 0;
+#pragma unroll
+        for (int w = 0; w < SORT_WARPS; w++) c += s_hist[w][d];
+        tile_hist[(size_t)blockIdx.x * RADIX_BINS + d] = c;
+    }
+}
+
+// ---- block-wide exclusive scan of one value per thread (256 threads) -----------------------------
+template <typename T>
+__device__ __forceinline__ T block_exclusive_scan(T v, T *s_warp /* [SORT_WARPS] */, T &total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    T incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        T n = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += n;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    T base = 0, tot = 0;
+#pragma unroll
+    for (int w = 0; w < SORT_WARPS; w++) {
+        T c = s_warp[w];
+        if (w < warp) base += c;
+        tot += c;
+    }
+    total = tot;
+    __syncthreads();
+    return base + incl - v;
+}
+
+// ---- per-genome scan of the tile histograms: (digit-major, tile-minor) exclusive offsets ----------
+__global__ void __launch_bounds__(RADIX_BINS)
+    k_radix_scan(const BatchGenome *__restrict__ genomes, uint32_t *__restrict__ tile_hist) {
+    __shared__ uint32_t s_warp[SORT_WARPS];
+    const BatchGenome G = genomes[blockIdx.x];
+    if (G.n_tiles == 0) return;
+    const int d = threadIdx.x;
+    uint32_t *col = tile_hist + (size_t)G.tile_first * RADIX_BINS + d;
+    uint32_t run = 0;
+#pragma unroll 8
+    for (uint32_t t = 0; t < G.n_tiles; t++) {
+        uint32_t c = col[(size_t)t * RADIX_BINS];
+        col[(size_t)t * RADIX_BINS] = run;
+        run += c;
+    }
+    uint32_t total;
+    uint32_t base = block_exclusive_scan<uint32_t>(run, s_warp, total);
+#pragma unroll 8
+    for (uint32_t t = 0; t < G.n_tiles; t++) col[(size_t)t * RADIX_BINS] += base;
+}
+
+// ---- stable scatter of one tile by one digit -------------------------------------------------------
+__global__ void __launch_bounds__(SORT_THREADS)
+    k_radix_scatter(const BatchGenome *__restrict__ genomes, uint32_t n_genomes, const uint64_t *__restrict__ in,
+                    uint64_t *__restrict__ out, const uint32_t *__restrict__ tile_offs, int shift, uint32_t dmask) {
+    __shared__ uint64_t s_keys[SORT_TILE];
+    __shared__ uint32_t s_cnt[SORT_WARPS][RADIX_BINS];
+    __shared__ uint32_t s_dstart[RADIX_BINS];
+    __shared__ uint32_t s_goff[RADIX_BINS];
+    __shared__ uint32_t s_warp[SORT_WARPS];
+    __shared__ uint32_t s_g;
+    if (threadIdx.x == 0) s_g = find_genome_s(genomes, n_genomes, blockIdx.x);
+    for (int i = threadIdx.x; i < SORT_WARPS * RADIX_BINS; i += SORT_THREADS) (&s_cnt[0][0])[i] = 0;
+    __syncthreads();
+    const BatchGenome G = genomes[s_g];
+    const uint32_t slot0 = (blockIdx.x - G.tile_first) * SORT_TILE;
+    const uint32_t count = min((uint32_t)SORT_TILE, G.n_slots - slot0);
+    const uint64_t *src = in + G.raw_off + slot0;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+
+    // warp w owns tile keys [w*512, (w+1)*512); item i of lane l is key w*512 + i*32 + l, so the
+    // (item, lane) order is the input order and the ranking below is stable.
+    uint64_t key[SORT_ITEMS];
+    uint32_t rank[SORT_ITEMS];
+#pragma unroll
+    for (int i = 0; i < SORT_ITEMS; i++) {
+        uint32_t idx = warp * (32 * SORT_ITEMS) + i * 32 + lane;
+        key[i] = idx < count ? src[idx] : KEY_SENTINEL;  // padding ranks after every real key
+    }
+#pragma unroll
+    for (int i = 0; i < SORT_ITEMS; i++) {
+        uint32_t d = (uint32_t)(key[i] >> shift) & dmask;
+        uint32_t peers = __match_any_sync(0xffffffffu, d);
+        uint32_t prev = s_cnt[warp][d];
+        __syncwarp();
+        rank[i] = prev + __popc(peers & lt_mask);
+        if (lane == __ffs(peers) - 1) s_cnt[warp][d] = prev + __popc(peers);
+        __syncwarp();
+    }
+    __syncthreads();
+    {   // thread d: exclusive scan over warps for digit d, then over digits
+        const int d = threadIdx.x;
+        uint32_t sum = 0;
+#pragma unroll
+        for (int w = 0; w < SORT_WARPS; w++) {
+            uint32_t c = s_cnt[w][d];
+            s_cnt[w][d] = sum;
+            sum += c;
+        }
+        uint32_t total;
+        uint32_t start = block_exclusive_scan<uint32_t>(sum, s_warp, total);
+        s_dstart[d] = start;
+        s_goff[d] = tile_offs[(size_t)blockIdx.x * RADIX_BINS + d];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < SORT_ITEMS; i++) {
+        uint32_t d = (uint32_t)(key[i] >> shift) & dmask;
+        s_keys[s_dstart[d] + s_cnt[warp][d] + rank[i]] = key[i];
+    }
+    __syncthreads();
+    uint64_t *dst = out + G.raw_off;
+#pragma unroll 4
+    for (uint32_t idx = threadIdx.x; idx < count; idx += SORT_THREADS) {
+        uint64_t kx = s_keys[idx];
+        uint32_t d = (uint32_t)(kx >> shift) & dmask;
+        dst[s_goff[d] + (idx - s_dstart[d])] = kx;
+    }
+}
+
+cudaError_t launch_sort(const BatchGenome *genomes, const SortPlan &plan, uint64_t **sorted_out, uint32_t *passes,
+                        cudaStream_t s) {
+    uint64_t *src = plan.keys_a, *dst = plan.keys_b;
+    uint32_t np = 0;
+    if (plan.n_tiles > 0) {
+        for (int shift = 0; shift < plan.key_bits; shift += RADIX_BITS) {
+            int bits = plan.key_bits - shift < RADIX_BITS ? plan.key_bits - shift : RADIX_BITS;
+            uint32_t dmask = (1u << bits) - 1u;
+            k_radix_hist<<<plan.n_tiles, SORT_THREADS, 0, s>>>(genomes, plan.n_genomes, src, plan.tile_hist, shift, dmask);
+            k_radix_scan<<<plan.n_genomes, RADIX_BINS, 0, s>>>(genomes, plan.tile_hist);
+            k_radix_scatter<<<plan.n_tiles, SORT_THREADS, 0, s>>>(genomes, plan.n_genomes, src, dst, plan.tile_hist, shift,
+                                                                  dmask);
+            uint64_t *t = src;
+            src = dst;
+            dst = t;
+            np++;
+        }
+    }
+    *sorted_out = src;
+    *passes = np;
+    return cudaGetLastError();
+}
+
+// ---- unique / compaction ---------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t reverse_pairs_u(uint64_t x) {
+    uint64_t y = __brevll(x);
+    return ((y >> 1) & 0x5555555555555555ull) | ((y & 0x5555555555555555ull) << 1);
+}
+
+// packed flags of one sorted position: low word = "first occurrence of a real key", high word = "and
+// it is its own reverse complement"
+__device__ __forceinline__ uint64_t unique_flags(const uint64_t *__restrict__ sorted, uint32_t idx, uint32_t n,
+                                                 bool check_pal, int k, uint64_t &key_out) {
+    if (idx >= n) {
+        key_out = KEY_SENTINEL;
+        return 0;
+    }
+    uint64_t kx = sorted[idx];
+    key_out = kx;
+    if (kx == KEY_SENTINEL) return 0;
+    if (idx > 0 && sorted[idx - 1] == kx) return 0;
+    uint64_t f = 1;
+    if (check_pal) {
+        uint64_t kmask = (k >= 32) ? ~0ull : ((1ull << (2 * k)) - 1);
+        uint64_t rc = (~(reverse_pairs_u(kx) >> (64 - 2 * k))) & kmask;
+        if (rc == kx) f |= 1ull << 32;
+    }
+    return f;
+}
+
+__global__ void __launch_bounds__(SORT_THREADS)
+    k_unique_count(const BatchGenome *__restrict__ genomes, uint32_t n_genomes, const uint64_t *__restrict__ sorted,
+                   uint64_t *__restrict__ tile_uniq, int check_pal, int k) {
+    __shared__ uint64_t s_warp[SORT_WARPS];
+    __shared__ uint32_t s_g;
+    if (threadIdx.x == 0) s_g = find_genome_s(genomes, n_genomes, blockIdx.x);
+    __syncthreads();
+    const BatchGenome G = genomes[s_g];
+    const uint32_t slot0 = (blockIdx.x - G.tile_first) * SORT_TILE;
+    const uint64_t *src = sorted + G.raw_off;
+    uint64_t acc = 0, kx;
+#pragma unroll 4
+    for (int i = 0; i < SORT_ITEMS; i++)
+        acc += unique_flags(src, slot0 + i * SORT_THREADS + threadIdx.x, G.n_slots, check_pal != 0, k, kx);
+    uint64_t total;
+    block_exclusive_scan<uint64_t>(acc, s_warp, total);
+    if (threadIdx.x == 0) tile_uniq[blockIdx.x] = total;
+}
+
+// one CTA per genome: exclusive scan of its tile counts in place, totals to genome_counts
+__global__ void __launch_bounds__(SORT_THREADS)
+    k_unique_scan(const BatchGenome *__restrict__ genomes, uint64_t *__restrict__ tile_uniq,
+                  uint64_t *__restrict__ genome_counts) {
+    __shared__ uint64_t s_warp[SORT_WARPS];
+    const BatchGenome G = genomes[blockIdx.x];
+    uint64_t carry = 0;
+    uint64_t *col = tile_uniq + G.tile_first;
+    for (uint32_t t0 = 0; t0 < G.n_tiles; t0 += SORT_THREADS) {
+        uint32_t t = t0 + threadIdx.x;
+        uint64_t v = t < G.n_tiles ? col[t] : 0;
+        uint64_t total;
+        uint64_t ex = block_exclusive_scan<uint64_t>(v, s_warp, total);
+        if (t < G.n_tiles) col[t] = carry + ex;
+        carry += total;
+    }
+    if (threadIdx.x == 0) genome_counts[blockIdx.x] = carry;
+}
+
+__global__ void __launch_bounds__(SORT_THREADS)
+    k_unique_write(const BatchGenome *__restrict__ genomes, uint32_t n_genomes, const uint64_t *__restrict__ sorted,
+                   const uint64_t *__restrict__ tile_uniq, const UniqueDst *__restrict__ dst, int check_pal, int k) {
+    __shared__ uint64_t s_warp[SORT_WARPS];
+    __shared__ uint32_t s_g;
+    if (threadIdx.x == 0) s_g = find_genome_s(genomes, n_genomes, blockIdx.x);
+    __syncthreads();
+    const BatchGenome G = genomes[s_g];
+    const UniqueDst D = dst[s_g];
+    const uint32_t slot0 = (blockIdx.x - G.tile_first) * SORT_TILE;
+    const uint64_t *src = sorted + G.raw_off;
+    uint64_t base = tile_uniq[blockIdx.x];
+    // chunks of 256 consecutive positions keep the output order == sorted order
+    for (int i = 0; i < SORT_ITEMS; i++) {
+        uint64_t kx;
+        uint64_t f = unique_flags(src, slot0 + i * SORT_THREADS + threadIdx.x, G.n_slots, check_pal != 0, k, kx);
+        uint64_t total;
+        uint64_t ex = block_exclusive_scan<uint64_t>(f, s_warp, total);
+        if (f & 1ull) {
+            uint64_t at = base + ex;
+            D.keys[(uint32_t)at] = kx;
+            if (f >> 32) D.pal_keys[(uint32_t)(at >> 32)] = kx;
+        }
+        base += total;
+    }
+}
+
+// sentinel tail of every set written by k_unique_write
+__global__ void __launch_bounds__(256)
+    k_unique_pad(const UniqueDst *__restrict__ dst, const uint64_t *__restrict__ genome_counts) {
+    const UniqueDst D = dst[blockIdx.x];
+    uint64_t c = genome_counts[blockIdx.x];
+    uint32_t n = (uint32_t)c, np = (uint32_t)(c >> 32);
+    uint32_t end = (uint32_t)set_padded(n);
+    for (uint32_t i = n + threadIdx.x; i < end; i += blockDim.x) D.keys[i] = KEY_SENTINEL;
+    if (D.pal_keys) {
+        uint32_t pend = (uint32_t)set_padded(np);
+        for (uint32_t i = np + threadIdx.x; i < pend; i += blockDim.x) D.pal_keys[i] = KEY_SENTINEL;
+    }
+}
+
+cudaError_t launch_unique_count(const BatchGenome *genomes, const SortPlan &plan, const uint64_t *sorted, int alphabet,
+                                int k, cudaStream_t s) {
+    if (plan.n_genomes == 0) return cudaSuccess;
+    int check_pal = (alphabet != GKD_PROT) && (k % 2 == 0);
+    if (plan.n_tiles)
+        k_unique_count<<<plan.n_tiles, SORT_THREADS, 0, s>>>(genomes, plan.n_genomes, sorted, plan.tile_uniq, check_pal, k);
+    k_unique_scan<<<plan.n_genomes, SORT_THREADS, 0, s>>>(genomes, plan.tile_uniq, plan.genome_counts);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_unique_write(const BatchGenome *genomes, const SortPlan &plan, const uint64_t *sorted,
+                                const UniqueDst *dst, int alphabet, int k, cudaStream_t s) {
+    if (plan.n_genomes == 0) return cudaSuccess;
+    int check_pal = (alphabet != GKD_PROT) && (k % 2 == 0);
+    if (plan.n_tiles)
+        k_unique_write<<<plan.n_tiles, SORT_THREADS, 0, s>>>(genomes, plan.n_genomes, sorted, plan.tile_uniq, dst,
+                                                             check_pal, k);
+    k_unique_pad<<<plan.n_genomes, 256, 0, s>>>(dst, plan.genome_counts);
+    return cudaGetLastError();
+}
+
+__global__ void k_fill_u64(uint64_t *dst, uint64_t n, uint64_t value) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
+        dst[i] = value;
+}
+
+cudaError_t launch_fill_u64(uint64_t *dst, uint64_t n, uint64_t value, cudaStream_t s) {
+    if (n == 0) return cudaSuccess;
+    uint64_t blocks = (n + 255) / 256;
+    if (blocks > 4096) blocks = 4096;
+    k_fill_u64<<<(unsigned)blocks, 256, 0, s>>>(dst, n, value);
+    return cudaGetLastError();
+}
+
+}  // namespace gkd

@@ -1,0 +1,229 @@
+"""Thin Python host layer over the C ABI: device memory plumbing for tests, bench and multi-GPU
+sharding.  The product is libgkd.so; nothing here computes."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Iterable, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _lib
+from ._lib import DNA, PROT, RNA, STRAND_BOTH, STRAND_CANONICAL, GkdConfig, GkdMetrics
+
+
+class GkdError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"gkd error {code}: {msg}")
+        self.code = code
+        self.msg = msg
+
+
+def _is_torch(x) -> bool:
+    return type(x).__module__.startswith("torch")
+
+
+class Engine:
+    """One gkd context on one GPU.
+
+    Mirrors the reference objects at batch granularity: `add` = `KmerType.createKmers` /
+    `new GenomeKmers(genome)` / `new ProteinKmers(str)`; `all_vs_all` = FastaDistanceProcessor's pair
+    loop; `query_vs_ref` = GenomeProcessor's; `pair` = `SequenceKmers.distance`.
+    """
+
+    def __init__(self, k: int = 0, alphabet: int = DNA, strand_mode: int = STRAND_BOTH, device: int = 0,
+                 workspace_bytes: int = 0, segment_keys: int = 0):
+        self._L = _lib.load()
+        cfg = GkdConfig(device=device, k=k, alphabet=alphabet, strand_mode=strand_mode,
+                        workspace_bytes=workspace_bytes, segment_keys=segment_keys)
+        h = C.c_void_p()
+        rc = self._L.gkd_create(C.byref(h), C.byref(cfg))
+        if rc:
+            raise GkdError(rc, (self._L.gkd_last_error(None) or b"").decode())
+        self._h = h
+        self.device = device
+        self.alphabet = alphabet
+        self._keep: List[object] = []
+
+    # -- plumbing ---------------------------------------------------------------------------------
+    def _ck(self, rc: int):
+        if rc:
+            raise GkdError(rc, (self._L.gkd_last_error(self._h) or b"").decode())
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.gkd_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    @staticmethod
+    def _ptr_len(x) -> Tuple[int, int, object]:
+        """(address, byte length, keep-alive) of str / bytes / numpy uint8 / torch uint8 (cpu or cuda)."""
+        if isinstance(x, str):
+            x = x.encode("latin-1")
+        if isinstance(x, (bytes, bytearray)):
+            buf = C.create_string_buffer(bytes(x), len(x)) if len(x) else C.create_string_buffer(1)
+            return C.addressof(buf), len(x), buf
+        if isinstance(x, np.ndarray):
+            a = np.ascontiguousarray(x).view(np.uint8)
+            return a.ctypes.data, a.size, a
+        if _is_torch(x):
+            t = x.contiguous()
+            return t.data_ptr(), t.numel() * t.element_size(), t
+        raise TypeError(f"unsupported sequence type {type(x)}")
+
+    # -- ingest ------------------------------------------------------------------------------------
+    def add(self, contigs) -> int:
+        """Add one genome / record; `contigs` is one sequence or a list of contigs (or proteins)."""
+        if isinstance(contigs, (str, bytes, bytearray, np.ndarray)) or _is_torch(contigs):
+            contigs = [contigs]
+        triples = [self._ptr_len(c) for c in contigs]
+        n = len(triples)
+        ptrs = (C.c_void_p * max(n, 1))(*[t[0] for t in triples])
+        lens = (C.c_uint64 * max(n, 1))(*[t[1] for t in triples])
+        out = C.c_uint32()
+        if any(_is_torch(c) and c.is_cuda for c in contigs):
+            import torch
+
+            torch.cuda.synchronize(self.device)  # producers ran on torch's stream
+        self._ck(self._L.gkd_add_sequences(self._h, ptrs, lens, n, C.byref(out)))
+        return out.value
+
+    def add_fasta(self, path: str, per_record: bool = True) -> Tuple[int, int]:
+        first, n = C.c_uint32(), C.c_uint32()
+        self._ck(self._L.gkd_add_fasta_file(self._h, path.encode(), 1 if per_record else 0, C.byref(first), C.byref(n)))
+        return first.value, n.value
+
+    def label(self, i: int) -> str:
+        return self._L.gkd_label(self._h, i).decode("latin-1")
+
+    def comment(self, i: int) -> str:
+        return self._L.gkd_comment(self._h, i).decode("latin-1")
+
+    def __len__(self) -> int:
+        return self._L.gkd_count(self._h)
+
+    # -- sets --------------------------------------------------------------------------------------
+    def build(self):
+        self._ck(self._L.gkd_build_sets(self._h))
+
+    def set_size(self, i: int) -> Tuple[int, int, int]:
+        """(reference HashSet size, canonical count, palindromes)"""
+        a, b, p = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        self._ck(self._L.gkd_set_size(self._h, i, C.byref(a), C.byref(b), C.byref(p)))
+        return a.value, b.value, p.value
+
+    def export_set(self, i: int) -> np.ndarray:
+        n = self.set_size(i)[1]
+        out = np.empty(n, dtype=np.uint64)
+        got = C.c_uint64()
+        self._ck(self._L.gkd_export_set(self._h, i, out.ctypes.data if n else None, n, C.byref(got)))
+        return out
+
+    def set_device_ptr(self, i: int) -> Tuple[int, int]:
+        p, n = C.c_void_p(), C.c_uint64()
+        self._ck(self._L.gkd_set_device_ptr(self._h, i, C.byref(p), C.byref(n)))
+        return (p.value or 0), n.value
+
+    def import_set(self, keys) -> int:
+        """Adopt a sorted key array (numpy uint64 on host or torch int64/uint64 on this device)."""
+        if isinstance(keys, np.ndarray):
+            a = np.ascontiguousarray(keys, dtype=np.uint64)
+            ptr, n, keep = a.ctypes.data, a.size, a
+        else:
+            import torch
+
+            t = keys.contiguous()
+            if t.is_cuda:
+                torch.cuda.synchronize(self.device)
+            ptr, n, keep = t.data_ptr(), t.numel(), t
+        out = C.c_uint32()
+        self._ck(self._L.gkd_import_set(self._h, ptr if n else None, n, C.byref(out)))
+        del keep
+        return out.value
+
+    # -- distances ---------------------------------------------------------------------------------
+    @staticmethod
+    def _outs(n: int, inter_out, dist_out, want_inter: bool, want_dist: bool):
+        inter = inter_out if inter_out is not None else (np.empty(n, dtype=np.uint64) if want_inter else None)
+        dist = dist_out if dist_out is not None else (np.empty(n, dtype=np.float64) if want_dist else None)
+
+        def addr(x):
+            if x is None:
+                return None
+            return x.ctypes.data if isinstance(x, np.ndarray) else x.data_ptr()
+
+        return inter, dist, addr(inter), addr(dist)
+
+    def all_vs_all(self, inter_out=None, dist_out=None, want_inter=True, want_dist=True):
+        n = len(self)
+        npairs = n * (n - 1) // 2
+        inter, dist, pi, pd = self._outs(npairs, inter_out, dist_out, want_inter, want_dist)
+        self._ck(self._L.gkd_all_vs_all(self._h, pi, pd))
+        return inter, dist
+
+    def all_vs_all_range(self, n: int, first: int, count: int, inter_out=None, dist_out=None):
+        inter, dist, pi, pd = self._outs(count, inter_out, dist_out, True, True)
+        self._ck(self._L.gkd_all_vs_all_range(self._h, n, first, count, pi, pd))
+        return inter, dist
+
+    def query_vs_ref(self, q: Sequence[int], r: Sequence[int]):
+        qa, ra = np.ascontiguousarray(q, dtype=np.uint32), np.ascontiguousarray(r, dtype=np.uint32)
+        inter, dist, pi, pd = self._outs(qa.size * ra.size, None, None, True, True)
+        self._ck(self._L.gkd_query_vs_ref(self._h, qa.ctypes.data, qa.size, ra.ctypes.data, ra.size, pi, pd))
+        return inter.reshape(qa.size, ra.size), dist.reshape(qa.size, ra.size)
+
+    def pairs(self, a: Sequence[int], b: Sequence[int]):
+        aa, ba = np.ascontiguousarray(a, dtype=np.uint32), np.ascontiguousarray(b, dtype=np.uint32)
+        inter, dist, pi, pd = self._outs(aa.size, None, None, True, True)
+        self._ck(self._L.gkd_pairs(self._h, aa.ctypes.data, ba.ctypes.data, aa.size, pi, pd))
+        return inter, dist
+
+    def pair(self, a: int, b: int) -> Tuple[int, int, float]:
+        i, u, d = C.c_uint64(), C.c_uint64(), C.c_double()
+        self._ck(self._L.gkd_pair(self._h, a, b, C.byref(i), C.byref(u), C.byref(d)))
+        return i.value, u.value, d.value
+
+    # -- misc --------------------------------------------------------------------------------------
+    def reset(self):
+        self._ck(self._L.gkd_reset(self._h))
+
+    @property
+    def stream_ptr(self) -> int:
+        """cudaStream_t of this context (wrap with torch.cuda.ExternalStream to time on it)"""
+        return self._L.gkd_stream(self._h) or 0
+
+    def metrics(self) -> dict:
+        m = GkdMetrics()
+        self._ck(self._L.gkd_get_metrics(self._h, C.byref(m)))
+        return {f: getattr(m, f) for f, _ in GkdMetrics._fields_ if not f.startswith("reserved")}
+
+
+def format_double(v: float) -> str:
+    buf = C.create_string_buffer(64)
+    _lib.load().gkd_format_double(v, buf, 64)
+    return buf.value.decode()
+
+
+def synth(dst, seed: int, family: int, member: int, rate: float, protein: bool = False, device: int = 0):
+    """Fill `dst` (numpy uint8 array or torch uint8 tensor, host or device) with a synthetic sequence."""
+    L = _lib.load()
+    if isinstance(dst, np.ndarray):
+        ptr, n, dev = dst.ctypes.data, dst.size, -1
+    else:
+        ptr, n, dev = dst.data_ptr(), dst.numel(), (device if dst.is_cuda else -1)
+    fn = L.gkd_synth_protein if protein else L.gkd_synth_dna
+    rc = fn(dev, ptr, n, seed, family, member, float(rate))
+    if rc:
+        raise GkdError(rc, "synth failed")
+    return dst

@@ -1,0 +1,168 @@
+/*
+ * gkd.h -- C ABI of libgkd.so, the B200 (sm_100a) k-mer set distance engine.
+ *
+ * This is the drop-in boundary for ONE path of SEEDtk/genome.distance: building per-genome k-mer
+ * sets and computing pairwise |A n B| and the reference's k-mer distance.  The reference (pure Java)
+ * has no FFI for this path; the boundary it exposes upward is the object API of the external
+ * org.theseed.sequence classes that its processors call.  Each entry point below names the
+ * reference call site(s) it stands behind (paths relative to
+ * /root/reference/src/main/java/org/theseed/genome/distance/).  Because one JNI crossing + one launch
+ * per SequenceKmers.distance() would be launch-bound, the engine is batched: the Java shim hands it
+ * whole genome lists and receives count/distance blocks (see INTEGRATION.md for the JNI binding).
+ *
+ * Conventions
+ *   - plain C types only; no exceptions or exit() cross the ABI; every call returns a gkd_status
+ *     (0 = OK, negative = error class) and leaves a message retrievable with gkd_last_error().
+ *   - caller owns every buffer it passes; inputs are consumed (copied to the device) before the
+ *     call returns; outputs are caller-allocated.  Input sequence pointers may be pageable host,
+ *     pinned host, or device memory (detected with cudaPointerGetAttributes).
+ *   - genomes/sequences are referred to by dense uint32 ids in insertion order.
+ *   - a context is single-caller (not thread-safe); different contexts are independent.
+ *   - there is NO CPU fallback: every entry point that computes fails with GKD_ECUDA when no
+ *     sm_100-class device is usable.
+ */
+#ifndef GKD_H
+#define GKD_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GKD_ABI_VERSION 1
+
+typedef enum gkd_status {
+    GKD_OK = 0,
+    GKD_EINVAL = -1, /* bad argument; the Java shim maps this to ParseFailureException */
+    GKD_EIO = -2,    /* unreadable input; maps to FileNotFoundException / IOException */
+    GKD_ENOMEM = -3, /* host or device allocation failed */
+    GKD_ECUDA = -4,  /* CUDA runtime / launch failure, or no usable device (sticky: poisons the ctx) */
+    GKD_ESTATE = -5  /* call made in the wrong phase (e.g. distances before gkd_build_sets) */
+} gkd_status;
+
+/* KmerType members (KmerType.DNA is the only constant visible in-tree, FastaDistanceProcessor.java:89;
+ * RNA reads u as t and is otherwise DNA; PROT is ProteinKmers) */
+typedef enum gkd_alphabet { GKD_DNA = 0, GKD_PROT = 1, GKD_RNA = 2 } gkd_alphabet;
+
+/* How set sizes and intersections are counted for nucleotide alphabets:
+ *   GKD_STRAND_BOTH      - reference semantics: the set holds the k-mers of the sequence and of its
+ *                          reverse complement, so |S| = 2|C| - P and I = 2|C_A n C_B| - P_I where C
+ *                          are canonical k-mers and P counts reverse-palindromic ones (even K only)
+ *   GKD_STRAND_CANONICAL - plain Jaccard over canonical k-mers (identical doubles for odd K)        */
+typedef enum gkd_strand_mode { GKD_STRAND_BOTH = 0, GKD_STRAND_CANONICAL = 1 } gkd_strand_mode;
+
+typedef struct gkd_config {
+    int32_t device;            /* CUDA device ordinal */
+    int32_t k;                 /* k-mer size; 0 = type default (21 DNA/RNA, 8 protein;
+                                  FastaDistanceProcessor.java:43,95-96).  DNA/RNA 1..32, protein 1..8 */
+    int32_t alphabet;          /* gkd_alphabet */
+    int32_t strand_mode;       /* gkd_strand_mode */
+    uint64_t workspace_bytes;  /* device scratch for set construction (0 = default 8 GiB cap) */
+    uint32_t segment_keys;     /* merge-path segment length in keys for the intersect kernel
+                                  (0 = choose from the workload) */
+    uint32_t reserved[7];
+} gkd_config;
+
+typedef struct gkd_ctx gkd_ctx;
+
+/* Throughput/byte counters of the last build / distance call (the numbers bench.py reports). */
+typedef struct gkd_metrics {
+    double pack_ms, encode_ms, sort_ms, unique_ms; /* kernels 1-3, CUDA-event time on the ctx stream */
+    double intersect_ms, epilogue_ms;              /* kernels 4-5 */
+    double h2d_ms, d2h_ms;                         /* host<->device copies issued by the engine */
+    uint64_t residues_packed;   /* bases / residues seen by kernel 1 */
+    uint64_t kmer_positions;    /* k-mer positions encoded by kernel 2 */
+    uint64_t keys_sorted;       /* keys through the radix sort (kernel 3 input) */
+    uint32_t sort_passes;       /* LSD passes per key */
+    uint32_t reserved0;
+    uint64_t keys_unique;       /* sum of |C| over the sets built */
+    uint64_t pairs;             /* pairs intersected by the last distance call */
+    uint64_t intersect_bytes;   /* ALGORITHMIC bytes of the last distance call: 8*(|C_A|+|C_B|) per pair */
+    uint64_t h2d_bytes, d2h_bytes;
+    uint64_t launches;          /* kernels launched by this ctx since creation */
+    uint64_t intersect_launches;
+    uint64_t reserved[6];
+} gkd_metrics;
+
+/* ---- lifecycle --------------------------------------------------------------------------- */
+/* new KmerType/GenomeKmers configuration: K is per-context instead of the reference's static
+ * GenomeKmers.setKmerSize / ProteinKmers.setKmerSize (GenomeProcessor.java:86, ProteinKmerReader.java:92) */
+int gkd_create(gkd_ctx **out, const gkd_config *cfg);
+int gkd_destroy(gkd_ctx *ctx);
+/* drop every genome and set but keep device pools warm (used between bench steps) */
+int gkd_reset(gkd_ctx *ctx);
+/* message of the last failure on ctx (ctx may be NULL for a failed gkd_create) */
+const char *gkd_last_error(const gkd_ctx *ctx);
+int gkd_abi_version(void);
+
+/* ---- ingest: kernel 1 --------------------------------------------------------------------- */
+/* One genome / sequence record from n_contigs pieces; k-mers never span pieces.
+ * Stands behind: new GenomeKmers(genome) (GenomeProcessor.java:109,139 - one piece per contig),
+ * KmerType.createKmers(seq, K) (FastaDistanceProcessor.java:153,184 - one piece),
+ * new ProteinKmers(str) (ProteinKmerReader.java:100-101 - one piece; or one piece per protein for a
+ * per-genome protein set).  Pointers may be host or device memory. */
+int gkd_add_sequences(gkd_ctx *ctx, const char *const *contigs, const uint64_t *lens, uint32_t n_contigs,
+                      uint32_t *out_id);
+/* FastaInputStream(File) (FastaDistanceProcessor.java:104-108,119-131): per_record=1 makes each FASTA
+ * record a unit (fastaDist); per_record=0 makes the whole file one genome, one contig per record. */
+int gkd_add_fasta_file(gkd_ctx *ctx, const char *path, int per_record, uint32_t *first_id, uint32_t *n_added);
+/* Sequence.getLabel()/getComment() (FastaDistanceProcessor.java:189-190); "" when not from FASTA */
+const char *gkd_label(const gkd_ctx *ctx, uint32_t id);
+const char *gkd_comment(const gkd_ctx *ctx, uint32_t id);
+uint32_t gkd_count(const gkd_ctx *ctx);
+
+/* ---- set construction: kernels 2 + 3 ------------------------------------------------------- */
+/* Build the sorted unique canonical uint64 key set of every genome added since the last build. */
+int gkd_build_sets(gkd_ctx *ctx);
+/* n_both = the reference's HashSet size (2|C|-P for DNA), n_canonical = |C|, n_palindromic = P */
+int gkd_set_size(const gkd_ctx *ctx, uint32_t id, uint64_t *n_both, uint64_t *n_canonical, uint64_t *n_palindromic);
+/* copy the sorted keys of one set to host memory (cap in keys); *n receives |C| */
+int gkd_export_set(gkd_ctx *ctx, uint32_t id, uint64_t *keys, uint64_t cap, uint64_t *n);
+/* device address of the sorted keys of one set (for NCCL exchange by the host layer) */
+int gkd_set_device_ptr(const gkd_ctx *ctx, uint32_t id, const uint64_t **keys, uint64_t *n);
+/* adopt a prebuilt sorted key array (host or device pointer; copied) as a new set, e.g. one received
+ * from another rank.  The unique/compact pass is re-run on it, which re-derives the palindrome list. */
+int gkd_import_set(gkd_ctx *ctx, const uint64_t *keys, uint64_t n, uint32_t *out_id);
+
+/* ---- distances: kernels 4 + 5 --------------------------------------------------------------- */
+/* All pairs i<j in id order, row-major strict upper triangle of length N*(N-1)/2
+ * (FastaDistanceProcessor.runReporter/computePairs :141-162,174-194).  inter receives the reference's
+ * similarity() value (both-strand count under GKD_STRAND_BOTH); either output may be NULL. */
+int gkd_all_vs_all(gkd_ctx *ctx, uint64_t *inter, double *dist);
+/* Every q[i] against every r[j], row-major nq*nr (GenomeProcessor.runReporter :129-147). */
+int gkd_query_vs_ref(gkd_ctx *ctx, const uint32_t *q, uint32_t nq, const uint32_t *r, uint32_t nr,
+                     uint64_t *inter, double *dist);
+/* Arbitrary pair list (the primitive the two calls above and the multi-GPU tile sharding use). */
+int gkd_pairs(gkd_ctx *ctx, const uint32_t *a, const uint32_t *b, uint64_t n_pairs, uint64_t *inter, double *dist);
+/* Sub-range [first, first+count) of the row-major strict-upper-triangle pair enumeration of the
+ * first n sets: the per-rank slice of the all-vs-all matrix. */
+int gkd_all_vs_all_range(gkd_ctx *ctx, uint32_t n, uint64_t first, uint64_t count, uint64_t *inter, double *dist);
+/* SequenceKmers.distance(other) for one pair (DistanceRepsProcessor.java:101,190;
+ * FastaDistanceRepsProcessor.java:128); uni = |A|+|B|-I */
+int gkd_pair(gkd_ctx *ctx, uint32_t a, uint32_t b, uint64_t *inter, uint64_t *uni, double *dist);
+
+/* ---- text + metrics --------------------------------------------------------------------------- */
+/* java.lang.Double.toString layout ("" + distance, FastaDistanceProcessor.java:189-190,
+ * GenomeProcessor.java:144); returns the length written, excluding the NUL */
+int gkd_format_double(double v, char *buf, size_t cap);
+int gkd_get_metrics(const gkd_ctx *ctx, gkd_metrics *out);
+/* the cudaStream_t every kernel and copy of this context is issued on (so a caller can bracket
+ * calls with its own CUDA events) */
+void *gkd_stream(const gkd_ctx *ctx);
+
+/* ---- synthetic genomes (bench/test utility; SURVEY section 8d generator) ----------------------- */
+/* Writes `len` lower-case bases of descendant `member` of ancestor `family` (per-base substitution
+ * probability sub_rate) to dst, which may be host or device memory.  Counter-based, so the host and
+ * device paths produce identical bytes. */
+int gkd_synth_dna(int device, char *dst, uint64_t len, uint64_t seed, uint32_t family, uint32_t member,
+                  double sub_rate);
+/* Same for a protein over the 20 standard amino-acid letters. */
+int gkd_synth_protein(int device, char *dst, uint64_t len, uint64_t seed, uint32_t family, uint32_t member,
+                      double sub_rate);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GKD_H */

@@ -1,0 +1,277 @@
+"""GPU parity tests proper: libgkd.so (through the C ABI) against the CPU oracle on the same inputs.
+
+Bar: bit-exact set sizes, keys, intersection counts and distances (the distance is computed with the
+same double formula, so equality is exact, not a tolerance).  PARITY UNPINNED by the reference itself
+(no golden vectors exist); the oracle is pinned to the SURVEY 8(c) known answers in test_oracle.py.
+"""
+import json
+import os
+import random
+
+import numpy as np
+import pytest
+
+import genome.distance_b200 as gkd
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden", "kat_survey_8c.json")
+
+
+def _rand_dna(rng, n, alphabet="acgt"):
+    return "".join(rng.choice(alphabet) for _ in range(n))
+
+
+def _mutate(rng, s, rate, alphabet="acgt"):
+    out = list(s)
+    for i in range(len(out)):
+        if rng.random() < rate:
+            out[i] = rng.choice(alphabet)
+    return "".join(out)
+
+
+def _np_family(seed, n_genomes, length, rates, protein=False):
+    """family-structured synthetic sequences from the engine's own generator (host path)"""
+    seqs = []
+    for g in range(n_genomes):
+        a = np.empty(length, dtype=np.uint8)
+        gkd.synth(a, seed, g % 3, g // 3, rates[g % len(rates)] if g // 3 else 0.0, protein=protein)
+        seqs.append(a.tobytes())
+    return seqs
+
+
+@pytest.mark.parametrize("kat", json.load(open(GOLD))["pairs"], ids=lambda k: k["name"])
+def test_kat_through_engine(orc, kat):
+    alpha = gkd.PROT if kat["alphabet"] == "PROT" else gkd.DNA
+    with gkd.Engine(k=kat["k"], alphabet=alpha) as e:
+        a, b = e.add(kat["a"]), e.add(kat["b"])
+        e.build()
+        inter, uni, dist = e.pair(a, b)
+        assert [e.set_size(a)[0], e.set_size(b)[0], inter] == kat["both"]
+        assert gkd.format_double(dist) == kat["distance"]
+        if "canonical" in kat:
+            assert [e.set_size(a)[1], e.set_size(b)[1]] == kat["canonical"][:2]
+        if "palindromes" in kat:
+            assert [e.set_size(a)[2], e.set_size(b)[2]] == kat["palindromes"][:2]
+        assert uni == kat["both"][0] + kat["both"][1] - inter
+
+
+@pytest.mark.parametrize("k", [1, 2, 3, 4, 5, 8, 11, 15, 16, 20, 21, 22, 27, 31, 32])
+def test_dna_sets_bit_exact(orc, k):
+    rng = random.Random(100 + k)
+    genomes = [
+        [_rand_dna(rng, 5000)],
+        [_rand_dna(rng, 3000, "ACGTacgtNn"), _rand_dna(rng, 700), "", _rand_dna(rng, k - 1 if k > 1 else 0), _rand_dna(rng, k)],
+        ["A" * 400 + "ACGT" * 100 + "T" * 300],                  # low complexity, tandem repeats, palindromes
+        [_rand_dna(rng, 9000, "acgtRYKMSWn-*")],                 # IUPAC and junk characters are skipped
+        [""],
+        [_rand_dna(rng, 33), _rand_dna(rng, 64), _rand_dna(rng, 31), _rand_dna(rng, 4097)],
+        [_rand_dna(rng, 70000)],
+    ]
+    with gkd.Engine(k=k) as e:
+        ids = [e.add(g) for g in genomes]
+        e.build()
+        osets = [orc.IntSet(g, k) for g in genomes]
+        for i, o in zip(ids, osets):
+            both, canon, pal = e.set_size(i)
+            assert (both, canon, pal) == (len(o), o.count, o.palindromes)
+            assert np.array_equal(e.export_set(i), o.keys())
+        inter, dist = e.all_vs_all()
+        t = 0
+        for i in range(len(genomes)):
+            for j in range(i + 1, len(genomes)):
+                assert int(inter[t]) == osets[i].similarity(osets[j]), (i, j)
+                assert dist[t] == osets[i].distance(osets[j])
+                t += 1
+    # string-set restatement agrees on a couple of the genomes too (both-strand sizes)
+    s0, s1 = orc.StrSet(genomes[0], k), orc.StrSet(genomes[1], k)
+    assert len(s0) == len(osets[0]) and len(s1) == len(osets[1])
+    assert s0.similarity(s1) == osets[0].similarity(osets[1])
+
+
+def test_rna_reads_u_as_t(orc):
+    rng = random.Random(5)
+    s = _rand_dna(rng, 4000, "acgu")
+    with gkd.Engine(k=9, alphabet=gkd.RNA) as e:
+        a = e.add(s)
+        b = e.add(s.replace("u", "t").upper())
+        e.build()
+        assert e.pair(a, b)[2] == 0.0
+        o = orc.IntSet(s, 9, orc.RNA)
+        assert np.array_equal(e.export_set(a), o.keys())
+
+
+@pytest.mark.parametrize("k", [1, 3, 7, 8])
+def test_protein_sets_bit_exact(orc, k):
+    rng = random.Random(200 + k)
+    aa = "ACDEFGHIKLMNPQRSTVWY"
+    proteomes = []
+    for g in range(5):
+        base = [_rand_dna(rng, rng.randint(0, 400), aa) for _ in range(30)]
+        proteomes.append(base)
+    proteomes.append([_mutate(rng, p, 0.1, aa) for p in proteomes[0]])
+    proteomes.append(["MKV", "", "X*xa" * 20])  # shorter than K, empty, odd characters stay literal
+    with gkd.Engine(k=k, alphabet=gkd.PROT) as e:
+        ids = [e.add(p) for p in proteomes]
+        e.build()
+        osets = [orc.IntSet(p, k, orc.PROT) for p in proteomes]
+        ssets = [orc.StrSet(p, k, orc.PROT) for p in proteomes]
+        for i, o, s in zip(ids, osets, ssets):
+            assert e.set_size(i) == (len(s), o.count, 0)
+            assert np.array_equal(e.export_set(i), o.keys())
+        qi, qd = e.query_vs_ref(ids[:4], ids[4:])
+        for a in range(4):
+            for b in range(len(ids) - 4):
+                assert int(qi[a, b]) == ssets[a].similarity(ssets[4 + b])
+                assert qd[a, b] == ssets[a].distance(ssets[4 + b])
+
+
+def test_all_vs_all_matches_command_oracle(orc):
+    seqs = _np_family(42, 12, 150000, [0.001, 0.01, 0.05, 0.2])
+    oi, od = orc.fasta_dist(seqs, 21, batch=20, threads=0, mode=1)
+    si, sd = orc.fasta_dist(seqs[:5], 21, batch=2, threads=0, mode=0)  # HashSet<String> analogue, rebuild path
+    with gkd.Engine(k=21) as e:
+        for s in seqs:
+            e.add(s)
+        e.build()
+        gi, gd = e.all_vs_all()
+        assert np.array_equal(gi, oi) and np.array_equal(gd, od)
+        assert (gd == 1.0).any() and (gd < 0.1).any()
+        # order-insensitive command semantics: any pair by explicit list gives the same answer
+        li, ld = e.pairs([0, 3, 4], [3, 0, 11])
+        assert li[0] == li[1] and ld[0] == ld[1]
+    with gkd.Engine(k=21) as e:
+        for s in seqs[:5]:
+            e.add(s)
+        e.build()
+        gi, gd = e.all_vs_all()
+        assert np.array_equal(gi, si) and np.array_equal(gd, sd)
+
+
+@pytest.mark.parametrize("k", [20, 21])
+def test_segmented_merge_path_is_exact(orc, k):
+    """Small merge-path segments (many (pair, segment) work items, global diagonal searches) must give
+    the same counts as whole-pair streaming and as the oracle -- including skewed sizes."""
+    lens = [1200000, 1200000, 90000, 2500000, 40]
+    seqs = []
+    for g, n in enumerate(lens):
+        a = np.empty(n, dtype=np.uint8)
+        gkd.synth(a, 9, 0, g, 0.02 if g else 0.0)
+        seqs.append(a.tobytes())
+    osets = [orc.IntSet(s, k) for s in seqs]
+    want_i = [osets[i].similarity(osets[j]) for i in range(len(seqs)) for j in range(i + 1, len(seqs))]
+    want_d = [osets[i].distance(osets[j]) for i in range(len(seqs)) for j in range(i + 1, len(seqs))]
+    for seg in (0, 2048, 5000, 65536, 1 << 22):
+        with gkd.Engine(k=k, segment_keys=seg) as e:
+            for s in seqs:
+                e.add(s)
+            e.build()
+            gi, gd = e.all_vs_all()
+            assert gi.tolist() == want_i, seg
+            assert gd.tolist() == want_d, seg
+
+
+def test_c1_full_size_pair_properties(orc):
+    """BASELINE config 1 at full size: 2 x 5 Mbp, K=21, against the oracle and the domain's invariants."""
+    import torch
+
+    n = 5_000_000
+    dev = torch.empty((3, n), dtype=torch.uint8, device="cuda")
+    gkd.synth(dev[0], 0x5EED0000, 1, 0, 0.0)
+    gkd.synth(dev[1], 0x5EED0000, 1, 1, 0.01)
+    host = dev[:2].cpu().numpy()
+    comp = np.zeros(256, dtype=np.uint8)
+    comp[list(b"acgt")] = list(b"tgca")
+    rc0 = comp[host[0][::-1]].copy()
+    with gkd.Engine(k=21) as e:
+        a, b = e.add(dev[0]), e.add(dev[1])       # device-resident inputs
+        c = e.add(rc0)                             # host input: reverse complement of genome 0
+        e.build()
+        oa, ob = orc.IntSet(host[0].tobytes(), 21), orc.IntSet(host[1].tobytes(), 21)
+        assert e.set_size(a) == (len(oa), oa.count, 0) and e.set_size(b) == (len(ob), ob.count, 0)
+        inter, uni, dist = e.pair(a, b)
+        assert inter == oa.similarity(ob) and dist == oa.distance(ob)
+        assert e.pair(b, a) == (inter, uni, dist)                    # symmetry
+        assert e.pair(a, a)[2] == 0.0                                # identity
+        assert e.pair(a, c)[2] == 0.0                                # reverse-complement invariance
+        assert np.array_equal(e.export_set(a), oa.keys())
+        assert 0.3 < dist < 0.4                                      # ~ 1 - 0.81/(2-0.81)
+
+
+def test_fasta_file_ingest(orc, tmp_path):
+    rng = random.Random(77)
+    recs = [("s1", "first record", _rand_dna(rng, 1000, "ACGT")), ("s2", "", _rand_dna(rng, 1300, "acgtn")),
+            ("s3", "two  words", ""), ("s4", "x", _rand_dna(rng, 777))]
+    text = ""
+    for label, comment, seq in recs:
+        text += ">" + label + (" " + comment if comment else "") + "\r\n"
+        for i in range(0, len(seq), 60):
+            text += seq[i:i + 60] + "\n"
+    p = tmp_path / "in.fa"
+    p.write_text(text)
+    parsed = orc.parse_fasta(text)
+    assert [(l, c, s) for l, c, s in parsed] == recs
+    with gkd.Engine(k=11) as e:
+        first, n = e.add_fasta(str(p))
+        assert (first, n) == (0, 4)
+        assert [(e.label(i), e.comment(i)) for i in range(4)] == [(l, c) for l, c, _ in recs]
+        e.build()
+        osets = [orc.IntSet(s, 11) for _, _, s in recs]
+        for i, o in enumerate(osets):
+            assert np.array_equal(e.export_set(i), o.keys())
+    with gkd.Engine(k=11) as e:  # whole file as one multi-contig genome
+        assert e.add_fasta(str(p), per_record=False) == (0, 1)
+        e.build()
+        o = orc.IntSet([s for _, _, s in recs], 11)
+        assert np.array_equal(e.export_set(0), o.keys())
+    with gkd.Engine(k=11) as e:
+        with pytest.raises(gkd.GkdError) as err:
+            e.add_fasta(str(tmp_path / "missing.fa"))
+        assert err.value.code == -2 and "not found or unreadable" in err.value.msg
+
+
+def test_import_export_and_ranges(orc):
+    seqs = _np_family(5, 9, 60000, [0.01, 0.05])
+    with gkd.Engine(k=21) as e, gkd.Engine(k=21) as f:
+        for s in seqs:
+            e.add(s)
+        e.build()
+        gi, gd = e.all_vs_all()
+        # ship the sets to a second context (the multi-GPU exchange path) and compare
+        for i in range(len(seqs)):
+            f.import_set(e.export_set(i))
+        fi, fd = f.all_vs_all()
+        assert np.array_equal(fi, gi) and np.array_equal(fd, gd)
+        # any contiguous slice of the pair enumeration reproduces the same numbers
+        total = len(gi)
+        for first, count in ((0, total), (0, 1), (5, 17), (total - 3, 3), (total, 0), (8, 1)):
+            ri, rd = f.all_vs_all_range(len(seqs), first, count)
+            assert np.array_equal(ri, gi[first:first + count]) and np.array_equal(rd, gd[first:first + count])
+        with pytest.raises(gkd.GkdError):
+            f.all_vs_all_range(len(seqs), total - 1, 5)
+
+
+def test_state_errors():
+    with gkd.Engine(k=21) as e:
+        e.add("ACGT" * 100)
+        with pytest.raises(gkd.GkdError) as err:
+            e.all_vs_all()
+        assert err.value.code == -5
+        e.build()
+        e.add("ACGT" * 50)
+        e.add("")
+        e.build()  # incremental build
+        inter, dist = e.all_vs_all()
+        assert dist[-1] == 1.0 and len(inter) == 3
+        e.reset()
+        assert len(e) == 0
+
+
+def test_synth_device_matches_host():
+    import torch
+
+    for protein in (False, True):
+        d = torch.empty(100003, dtype=torch.uint8, device="cuda")
+        h = np.empty(100003, dtype=np.uint8)
+        gkd.synth(d, 3, 4, 2, 0.07, protein=protein)
+        gkd.synth(h, 3, 4, 2, 0.07, protein=protein)
+        assert np.array_equal(d.cpu().numpy(), h)
