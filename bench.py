@@ -1,0 +1,348 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the k-mer set distance hot path (BASELINE.json metric).
+
+Workload (config.workload): BASELINE configs[1] -- N synthetic 5 Mbp genomes (10 families of mutated
+descendants, SURVEY 8d generator), DNA K=21, all-vs-all Jaccard distance = N(N-1)/2 pairs.  Default
+N=1000 (499,500 pairs) on one B200.  One "step" = one full pass of the hot path: kernel 1 (pack) ->
+2 (canonical encode) -> 3 (radix sort + unique) -> 4 (merge-path intersect) -> 5 (distance epilogue).
+
+  value  : pairs/s with the genome text already resident in HBM when the step starts
+  e2e    : pairs/s through the C ABI with HOST (pinned) text buffers in, host result arrays out
+  roofline: k_intersect algorithmic bytes 8*(|A|+|B|) per pair / CUDA-event time of the launch
+  cpu_baseline: the oracle's HashSet<String> port of the reference on a bounded sample (rank 0, N=1)
+
+N>1 (torchrun): strong scaling of the same workload -- rank r builds the sets of its slice of the
+genomes, the set arenas are exchanged over NCCL (one broadcast per owner), every rank intersects its
+contiguous slice of the pair enumeration; no cross-rank reduction.
+
+`--impl reference` times the reference's own CPU algorithm (oracle string-set port; the Java
+original cannot run here: no JVM, arithmetic in an un-vendored artifact) on a bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "genome pairs/sec all-vs-all k-mer distance"
+UNIT = "pairs/s"
+SEED = 0x5EED0000
+RATES = [0.001, 0.01, 0.05, 0.2]
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--genomes", type=int, default=int(os.environ.get("GKD_BENCH_GENOMES", "1000")))
+    ap.add_argument("--length", type=int, default=int(os.environ.get("GKD_BENCH_LENGTH", "5000000")))
+    ap.add_argument("--families", type=int, default=10)
+    ap.add_argument("--k", type=int, default=21)
+    ap.add_argument("--cpu-sample", type=int, default=int(os.environ.get("GKD_BENCH_CPU_SAMPLE", "8")))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def genome_params(g: int, n_genomes: int, families: int):
+    """family / member / substitution rate of genome g (10 families x 100 at the default size)"""
+    per = max(1, (n_genomes + families - 1) // families)
+    fam, mem = g // per, g % per
+    rate = 0.0 if mem == 0 else RATES[mem % len(RATES)]
+    return fam, mem, rate
+
+
+def workload_name(a):
+    return (f"{a.genomes} synthetic {a.length / 1e6:g} Mbp genomes all-vs-all DNA k-mer Jaccard, K={a.k} "
+            f"({a.genomes * (a.genomes - 1) // 2} pairs)")
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx = gpu_index
+        self.proc = None
+        self.path = f"/tmp/gkd_clocks_{os.getpid()}.csv"
+
+    def start(self):
+        try:
+            self.f = open(self.path, "w")
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.idx)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return None
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.f.close()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        try:
+            for line in open(self.path):
+                p = [x.strip() for x in line.split(",")]
+                if len(p) < 9:
+                    continue
+                try:
+                    sm.append(float(p[1]))
+                    mx.append(float(p[2]))
+                except ValueError:
+                    continue
+                for name, v in zip(names, p[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if not sm:
+            return None
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline (oracle port; the only place bench.py executes oracle/)
+# ------------------------------------------------------------------------------------------------
+def host_sample(a, n_sample: int):
+    import numpy as np
+
+    import genome.distance_b200 as gkd
+
+    seqs = []
+    for g in range(n_sample):
+        fam, mem, rate = genome_params(g, a.genomes, a.families)
+        buf = np.empty(a.length, dtype=np.uint8)
+        gkd.synth(buf, SEED, fam, mem, rate)
+        seqs.append(buf.tobytes())
+    return seqs
+
+
+def run_cpu_reference(a, n_sample: int):
+    """FastaDistanceProcessor's algorithm (HashSet<String> port, rows in parallel) on the first
+    n_sample genomes of the workload; returns (pairs/s, seconds, threads, pairs)."""
+    from oracle import oracle as orc
+
+    seqs = host_sample(a, n_sample)
+    threads = orc.max_threads()
+    t0 = time.perf_counter()
+    orc.fasta_dist(seqs, a.k, alphabet=orc.DNA, batch=20, threads=threads, mode=0)
+    dt = time.perf_counter() - t0
+    pairs = n_sample * (n_sample - 1) // 2
+    return pairs / dt, dt, threads, pairs
+
+
+def reference_main(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    vals = []
+    threads = pairs = 0
+    for s in range(a.warmup + a.steps):
+        v, dt, threads, pairs = run_cpu_reference(a, a.cpu_sample)
+        if s >= a.warmup:
+            vals.append((v, dt))
+    value = sum(p for p, _ in vals) / len(vals)
+    ms = 1e3 * sum(d for _, d in vals) / len(vals)
+    sample = (f"first {a.cpu_sample} genomes of the workload ({pairs} pairs/step), batch=20 so every set is cached "
+              f"(no per-pair rebuilds: favourable to the CPU); C port of the reference's HashSet<String> algorithm, "
+              f"not the JVM")
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
+            "warmup": a.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "u64", "data": "synthetic", "config": {"workload": workload_name(a), "k": a.k},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+def main():
+    a = parse_args()
+    if a.impl == "reference":
+        return reference_main(a)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import genome.distance_b200 as gkd
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a GPU: libgkd has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    from genome.distance_b200 import sharding
+
+    N, Lg = a.genomes, a.length
+    total_pairs = N * (N - 1) // 2
+    my_ids = sharding.genome_slice(N, world, rank)
+    first_pair, n_my_pairs = sharding.pair_slice(total_pairs, world, rank)
+
+    # synthetic inputs: this rank's genomes as text in HBM, and a pinned host copy for the e2e leg
+    d_text = torch.empty((len(my_ids), Lg), dtype=torch.uint8, device=dev)
+    for r, g in enumerate(my_ids):
+        fam, mem, rate = genome_params(g, N, a.families)
+        gkd.synth(d_text[r], SEED, fam, mem, rate, device=local)
+    h_text = None
+    if not a.no_e2e:
+        h_text = torch.empty((len(my_ids), Lg), dtype=torch.uint8, pin_memory=True)
+        h_text.copy_(d_text)
+    torch.cuda.synchronize()
+
+    eng = gkd.Engine(k=a.k, device=local)
+    ext = torch.cuda.ExternalStream(eng.stream_ptr, device=dev)
+    inter = np.empty(n_my_pairs, dtype=np.uint64)
+    dist_out = np.empty(n_my_pairs, dtype=np.float64)
+
+    def one_step(text):
+        """one pass of the hot path over the whole workload; returns engine metrics"""
+        eng.reset()
+        for r in range(len(my_ids)):
+            eng.add(text[r])
+        eng.build()
+        if world > 1:
+            id_map = sharding.exchange_sets(eng, N, world, rank, dev)
+            ia, ib = sharding.local_pair_ids(id_map, N, first_pair, n_my_pairs)
+            eng.pairs(ia, ib, inter_out=inter, dist_out=dist_out)
+        else:
+            eng.all_vs_all_range(N, first_pair, n_my_pairs, inter_out=inter, dist_out=dist_out)
+        return eng.metrics()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(text, steps):
+        """(max-over-ranks seconds for `steps` steps on the device, per-step metrics)"""
+        mets = []
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record(ext)
+        for _ in range(steps):
+            mets.append(one_step(text))
+        e1.record(ext)
+        barrier()
+        wall = time.perf_counter() - t0
+        dev_s = e0.elapsed_time(e1) / 1e3
+        t = torch.tensor([dev_s, wall], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0]), float(t[1]), mets
+
+    # warm-up (also sizes every pool), then the timed region with the clock sampler running
+    launches0 = None
+    for _ in range(a.warmup):
+        m = one_step(d_text)
+    launches0 = eng.metrics()["launches"]
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    dev_s, wall_s, mets = timed(d_text, a.steps)
+    clocks = sampler.stop() if sampler else None
+    launches = eng.metrics()["launches"] - launches0
+
+    value = a.steps * total_pairs / dev_s
+    ms_per_step = 1e3 * dev_s / a.steps
+
+    # e2e: same step from pinned host text (H2D inside), results to host arrays (D2H inside)
+    e2e = None
+    if h_text is not None:
+        one_step(h_text)  # one warm-up of the host path (pinned staging, pools)
+        e_dev, e_wall, emets = timed(h_text, a.steps)
+        e_s = max(e_dev, e_wall)
+        h2d = sum(m["h2d_bytes"] for m in emets) / a.steps
+        d2h = sum(m["d2h_bytes"] for m in emets) / a.steps
+        if world > 1:
+            t = torch.tensor([h2d, d2h], dtype=torch.float64, device=dev)
+            dist.all_reduce(t)
+            h2d, d2h = float(t[0]), float(t[1])
+        e2e = {"value": a.steps * total_pairs / e_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+               "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * e_s / a.steps}
+
+    # roofline of the dominant kernel (k_intersect), from the engine's CUDA events on its own stream
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    isect_ms = sum(m["intersect_ms"] for m in mets) / len(mets)
+    isect_bytes = sum(m["intersect_bytes"] for m in mets) / len(mets)
+    achieved = isect_bytes / (isect_ms * 1e-3) / 1e9 if isect_ms > 0 else 0.0
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "intersect_traffic.json")
+    if os.path.exists(tpath):
+        try:
+            tj = json.load(open(tpath))
+            # measured DRAM bytes per algorithmic byte on the profiled launch, scaled to this launch
+            traffic = tj["dram_bytes_per_algorithmic_byte"] * isect_bytes
+        except Exception:
+            traffic = None
+    roofline = {"kernel": "k_intersect", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": isect_bytes, "ms_per_launch": isect_ms,
+                "note": "achieved = 8*(|A|+|B|) bytes per pair / CUDA-event time; rows served from L2 can push it past HBM peak"}
+    build_ms = sum(m["encode_ms"] + m["sort_ms"] + m["unique_ms"] for m in mets) / len(mets)
+    kpos = sum(m["kmer_positions"] for m in mets) / len(mets)
+    stages = {"encode_ms": sum(m["encode_ms"] for m in mets) / len(mets),
+              "sort_ms": sum(m["sort_ms"] for m in mets) / len(mets),
+              "unique_ms": sum(m["unique_ms"] for m in mets) / len(mets),
+              "intersect_ms": isect_ms, "epilogue_ms": sum(m["epilogue_ms"] for m in mets) / len(mets),
+              "kmers_hashed_per_s_this_rank": kpos / (build_ms * 1e-3) if build_ms > 0 else 0.0,
+              "sort_passes": mets[-1]["sort_passes"]}
+
+    cpu = None
+    if rank == 0 and world == 1 and not a.no_cpu_baseline:
+        v, dt, threads, pairs = run_cpu_reference(a, a.cpu_sample)
+        cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
+               "sample": f"first {a.cpu_sample} genomes of the workload, {pairs} pairs in {dt:.1f} s; HashSet<String> port "
+                         f"of FastaDistanceProcessor (batch=20, all sets cached: favourable to the CPU); not the JVM"}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "dtype": "u64", "data": "synthetic",
+                "config": {"workload": workload_name(a), "k": a.k, "genomes": N, "genome_bp": Lg, "pairs": total_pairs,
+                           "families": a.families, "sharding": f"pair-range x{world}" if world > 1 else "single GPU",
+                           "l2": "inputs (40 MB per set, 40 GB total) are far larger than L2; no flush needed"},
+                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
+                "clocks": clocks, "stages": stages, "wall_s_timed_region": wall_s}
+        print(json.dumps(line), flush=True)
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -439,7 +439,6 @@ int run_pairs(gkd_ctx *c, const HostPairs &hp, uint64_t *inter, double *dist) {
     c->m.pairs = hp.count;
     c->m.intersect_bytes = 0;
     c->m.intersect_ms = c->m.epilogue_ms = 0;
-    if (hp.count == 0) return GKD_OK;
 
     // validate ids, gather sizes for the segmenting decision and the byte accounting
     uint64_t max_n = 0;
@@ -451,8 +450,8 @@ int run_pairs(gkd_ctx *c, const HostPairs &hp, uint64_t *inter, double *dist) {
             max_n = std::max<uint64_t>(max_n, size_of(i));
         }
         // bytes of the requested range, row by row
-        uint32_t i0, j0;
-        upper_pair(hp.first, hp.n, i0, j0);
+        uint32_t i0 = 0, j0 = 1;
+        if (hp.count) upper_pair(hp.first, hp.n, i0, j0);
         uint64_t left = hp.count;
         std::vector<uint64_t> prefix(hp.n + 1, 0);
         for (uint32_t i = 0; i < hp.n; i++) prefix[i + 1] = prefix[i] + size_of(i);
@@ -484,6 +483,7 @@ int run_pairs(gkd_ctx *c, const HostPairs &hp, uint64_t *inter, double *dist) {
         }
     }
     c->m.intersect_bytes = (uint64_t)sum_bytes;
+    if (hp.count == 0) return GKD_OK;
 
     // merge-path segmenting: whole pairs when there are enough of them to fill the machine
     const uint64_t max_l = std::max<uint64_t>(2 * max_n, 1);

@@ -135,6 +135,19 @@ class Engine:
         self._ck(self._L.gkd_set_device_ptr(self._h, i, C.byref(p), C.byref(n)))
         return (p.value or 0), n.value
 
+    def set_tensor(self, i: int):
+        """zero-copy 1-D int64 torch view of the sorted keys of set i on this context's device"""
+        import torch
+
+        ptr, n = self.set_device_ptr(i)
+        if n == 0:
+            return torch.empty(0, dtype=torch.int64, device=f"cuda:{self.device}")
+
+        class _Raw:
+            __cuda_array_interface__ = {"shape": (n,), "typestr": "<i8", "data": (ptr, False), "version": 3}
+
+        return torch.as_tensor(_Raw(), device=f"cuda:{self.device}")
+
     def import_set(self, keys) -> int:
         """Adopt a sorted key array (numpy uint64 on host or torch int64/uint64 on this device)."""
         if isinstance(keys, np.ndarray):
@@ -183,9 +196,9 @@ class Engine:
         self._ck(self._L.gkd_query_vs_ref(self._h, qa.ctypes.data, qa.size, ra.ctypes.data, ra.size, pi, pd))
         return inter.reshape(qa.size, ra.size), dist.reshape(qa.size, ra.size)
 
-    def pairs(self, a: Sequence[int], b: Sequence[int]):
+    def pairs(self, a: Sequence[int], b: Sequence[int], inter_out=None, dist_out=None):
         aa, ba = np.ascontiguousarray(a, dtype=np.uint32), np.ascontiguousarray(b, dtype=np.uint32)
-        inter, dist, pi, pd = self._outs(aa.size, None, None, True, True)
+        inter, dist, pi, pd = self._outs(aa.size, inter_out, dist_out, True, True)
         self._ck(self._L.gkd_pairs(self._h, aa.ctypes.data, ba.ctypes.data, aa.size, pi, pd))
         return inter, dist
 
