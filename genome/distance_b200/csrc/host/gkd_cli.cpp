@@ -1,0 +1,440 @@
+// gkd_cli.cpp -- the `gkd` command: C++ mirror of the two reference sub-commands on the hot path,
+// with the reference's option names, defaults, validation messages, headers and number format.
+//
+//   fastaDist  -> FastaDistanceProcessor.java  (options :66-90, validation :93-112, report :134-194)
+//   genomes    -> GenomeProcessor.java         (options :54-79, validation :82-116, report :119-150)
+//
+// Dispatch mirrors App.java:35-111 (args[0] selects the processor).  Reports go to stdout or -o,
+// log lines to stderr (logback.xml:4-13).  Every distance comes from libgkd.so; there is no CPU path.
+#include <dirent.h>
+#include <sys/stat.h>
+
+#include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstring>
+#include <ctime>
+#include <fstream>
+#include <iostream>
+#include <map>
+#include <sstream>
+
+#include "kmers.hpp"
+
+using namespace theseed;
+
+namespace {
+
+void logInfo(const std::string &msg) {
+    auto now = std::chrono::system_clock::now();
+    std::time_t t = std::chrono::system_clock::to_time_t(now);
+    auto ms = std::chrono::duration_cast<std::chrono::milliseconds>(now.time_since_epoch()).count() % 1000;
+    char buf[64];
+    std::strftime(buf, sizeof(buf), "%Y-%m-%d %H:%M:%S", std::localtime(&t));
+    fprintf(stderr, "%s,%03d [main] %s\n", buf, (int)ms, msg.c_str());  // "%date [%thread] %msg%n"
+}
+
+std::string javaDouble(double v) {
+    char buf[64];
+    gkd_format_double(v, buf, sizeof(buf));
+    return buf;
+}
+
+bool readable(const std::string &p) {
+    std::ifstream f(p);
+    return f.good();
+}
+bool exists(const std::string &p) {
+    struct stat st;
+    return stat(p.c_str(), &st) == 0;
+}
+bool isDir(const std::string &p) {
+    struct stat st;
+    return stat(p.c_str(), &st) == 0 && S_ISDIR(st.st_mode);
+}
+
+// ---- args4j-style option table -----------------------------------------------------------------
+struct OptSpec {
+    std::vector<std::string> names;
+    bool takesValue;
+    std::string usage;
+};
+
+struct Parsed {
+    std::map<std::string, std::string> values;  // keyed by first name
+    std::vector<std::string> positional;
+};
+
+Parsed parseOptions(const std::vector<OptSpec> &specs, const std::vector<std::string> &args) {
+    Parsed out;
+    for (size_t i = 0; i < args.size(); i++) {
+        const std::string &a = args[i];
+        if (a.size() > 1 && a[0] == '-' && !(a.size() > 1 && (isdigit((unsigned char)a[1]) || a[1] == '.'))) {
+            const OptSpec *hit = nullptr;
+            for (auto &s : specs)
+                for (auto &n : s.names)
+                    if (n == a) hit = &s;
+            if (!hit) throw ParseFailureException("\"" + a + "\" is not a valid option");
+            if (hit->takesValue) {
+                if (i + 1 >= args.size()) throw ParseFailureException("Option \"" + a + "\" takes an operand");
+                out.values[hit->names[0]] = args[++i];
+            } else {
+                out.values[hit->names[0]] = "true";
+            }
+        } else {
+            out.positional.push_back(a);
+        }
+    }
+    return out;
+}
+
+int toInt(const std::string &name, const std::string &v) {
+    try {
+        size_t pos = 0;
+        int r = std::stoi(v, &pos);
+        if (pos != v.size()) throw std::invalid_argument(v);
+        return r;
+    } catch (...) {
+        throw ParseFailureException("\"" + v + "\" is not a valid value for \"" + name + "\"");
+    }
+}
+double toDouble(const std::string &name, const std::string &v) {
+    try {
+        size_t pos = 0;
+        double r = std::stod(v, &pos);
+        if (pos != v.size()) throw std::invalid_argument(v);
+        return r;
+    } catch (...) {
+        throw ParseFailureException("\"" + v + "\" is not a valid value for \"" + name + "\"");
+    }
+}
+
+void printUsage(const std::string &cmd, const std::vector<OptSpec> &specs, const std::string &positional) {
+    fprintf(stderr, "usage: gkd %s [options] %s\n", cmd.c_str(), positional.c_str());
+    for (auto &s : specs) {
+        std::string names;
+        for (auto &n : s.names) names += (names.empty() ? "" : ", ") + n;
+        fprintf(stderr, "  %-34s %s\n", names.c_str(), s.usage.c_str());
+    }
+}
+
+// ---- fastaDist -----------------------------------------------------------------------------------
+const std::vector<OptSpec> FASTA_OPTS = {
+    {{"--input", "-i"}, true, "input FASTA file (if not STDIN)"},
+    {{"--kSize", "--kmerSize", "-K"}, true, "kmer size to use; 0 for sequence type default"},
+    {{"--batch", "-b"}, true, "batch size for kmer cache and parallelism"},
+    {{"--type"}, true, "input sequence type"},
+    {{"--output", "-o"}, true, "output file for report (if not STDOUT)"},
+    {{"--device"}, true, "CUDA device ordinal (additive option; default 0)"},
+    {{"--help", "-h"}, false, "display command-line usage"},
+    {{"--verbose", "-v"}, false, "display more frequent log messages"},
+};
+
+int fastaDist(const std::vector<std::string> &args) {
+    Parsed p = parseOptions(FASTA_OPTS, args);
+    if (p.values.count("--help")) {
+        printUsage("fastaDist", FASTA_OPTS, "");
+        return 0;
+    }
+    // setReporterDefaults (:85-90)
+    std::string inFile = p.values.count("--input") ? p.values["--input"] : "";
+    int kmerSize = p.values.count("--kSize") ? toInt("--kSize", p.values["--kSize"]) : 0;
+    int batchSize = p.values.count("--batch") ? toInt("--batch", p.values["--batch"]) : 20;
+    KmerType seqType = p.values.count("--type") ? parseKmerType(p.values["--type"]) : KmerType::DNA;
+    int device = p.values.count("--device") ? toInt("--device", p.values["--device"]) : 0;
+    // validateReporterParms (:93-112)
+    if (kmerSize == 0) kmerSize = kmerTypeDefaultK(seqType);
+    if (kmerSize < 2) throw ParseFailureException("Kmer size must be at least 2.");
+    if (batchSize < 1) throw ParseFailureException("Batch size must be at least 1.");
+    const char *typeName = seqType == KmerType::DNA ? "DNA" : (seqType == KmerType::RNA ? "RNA" : "PROT");
+    if (inFile.empty()) logInfo(std::string("Reading ") + typeName + " sequences from the standard input.");
+    else if (!readable(inFile)) throw IOException("Input file " + inFile + " is not found or unreadable.");
+    else logInfo(std::string("Reading ") + typeName + " sequences from " + inFile + ".");
+    std::ofstream ofile;
+    if (p.values.count("--output")) {
+        ofile.open(p.values["--output"]);
+        if (!ofile) throw IOException("Cannot open output file " + p.values["--output"] + ".");
+    }
+    std::ostream &writer = p.values.count("--output") ? (std::ostream &)ofile : std::cout;
+
+    KmerEngine engine(seqType, kmerSize, device);
+    std::vector<SequenceKmers> seqs = engine.addFasta(inFile.empty() ? "-" : inFile);
+    logInfo(std::to_string(seqs.size()) + " sequences read from input.");
+    // runReporter (:134-165): the batch cache and the per-row parallel streams are what the engine
+    // replaces; every pair i<j is computed in one batched launch and printed in list order
+    writer << "seq1\tname1\tseq2\tname2\tdistance\n";
+    engine.build();
+    logInfo(std::to_string(seqs.size()) + " sequences cached. Computing distances.");
+    std::vector<double> dist;
+    engine.allVsAll(nullptr, dist);
+    size_t t = 0;
+    std::string line;
+    for (size_t i = 0; i < seqs.size(); i++) {
+        for (size_t j = i + 1; j < seqs.size(); j++, t++) {
+            line.clear();
+            line += seqs[i].getGenomeId();
+            line += '\t';
+            line += seqs[i].getGenomeName();
+            line += '\t';
+            line += seqs[j].getGenomeId();
+            line += '\t';
+            line += seqs[j].getGenomeName();
+            line += '\t';
+            line += javaDouble(dist[t]);
+            line += '\n';
+            writer << line;
+        }
+    }
+    writer.flush();
+    logInfo(std::to_string(t) + " pairs computed in 1 batches.");
+    return 0;
+}
+
+// ---- GTO reader (GenomeSource.Type.DIR: a directory of *.gto JSON files) ---------------------------
+struct JsonCursor {
+    const std::string &s;
+    size_t p = 0;
+    explicit JsonCursor(const std::string &str) : s(str) {}
+    void ws() {
+        while (p < s.size() && isspace((unsigned char)s[p])) p++;
+    }
+    bool eat(char c) {
+        ws();
+        if (p < s.size() && s[p] == c) {
+            p++;
+            return true;
+        }
+        return false;
+    }
+    std::string str() {
+        ws();
+        if (p >= s.size() || s[p] != '"') throw IOException("malformed GTO: string expected");
+        p++;
+        std::string out;
+        while (p < s.size() && s[p] != '"') {
+            if (s[p] == '\\' && p + 1 < s.size()) {
+                char e = s[p + 1];
+                p += 2;
+                switch (e) {
+                case 'n': out += '\n'; break;
+                case 't': out += '\t'; break;
+                case 'r': out += '\r'; break;
+                case 'u': p += 4; out += '?'; break;
+                default: out += e;
+                }
+            } else out += s[p++];
+        }
+        p++;
+        return out;
+    }
+    void skip() {
+        ws();
+        if (p >= s.size()) return;
+        char c = s[p];
+        if (c == '"') {
+            str();
+        } else if (c == '{' || c == '[') {
+            char close = c == '{' ? '}' : ']';
+            p++;
+            if (eat(close)) return;
+            do {
+                if (c == '{') {
+                    str();
+                    if (!eat(':')) throw IOException("malformed GTO: ':' expected");
+                }
+                skip();
+            } while (eat(','));
+            if (!eat(close)) throw IOException("malformed GTO: unbalanced brackets");
+        } else {
+            while (p < s.size() && s[p] != ',' && s[p] != '}' && s[p] != ']' && !isspace((unsigned char)s[p])) p++;
+        }
+    }
+};
+
+struct GenomeData {
+    std::string id, name;
+    std::vector<std::string> contigs;
+};
+
+GenomeData readGto(const std::string &path) {
+    std::ifstream f(path, std::ios::binary);
+    if (!f) throw IOException("Cannot read genome file " + path + ".");
+    std::stringstream ss;
+    ss << f.rdbuf();
+    std::string text = ss.str();
+    JsonCursor c(text);
+    GenomeData g;
+    if (!c.eat('{')) throw IOException("malformed GTO " + path);
+    if (!c.eat('}')) {
+        do {
+            std::string key = c.str();
+            if (!c.eat(':')) throw IOException("malformed GTO " + path);
+            if (key == "id") g.id = c.str();
+            else if (key == "scientific_name") g.name = c.str();
+            else if (key == "contigs") {
+                if (!c.eat('[')) throw IOException("malformed GTO " + path + ": contigs is not a list");
+                if (!c.eat(']')) {
+                    do {
+                        if (!c.eat('{')) throw IOException("malformed GTO " + path + ": contig is not an object");
+                        if (!c.eat('}')) {
+                            do {
+                                std::string ck = c.str();
+                                if (!c.eat(':')) throw IOException("malformed GTO " + path);
+                                if (ck == "dna") g.contigs.push_back(c.str());
+                                else c.skip();
+                            } while (c.eat(','));
+                            if (!c.eat('}')) throw IOException("malformed GTO " + path);
+                        }
+                    } while (c.eat(','));
+                    if (!c.eat(']')) throw IOException("malformed GTO " + path);
+                }
+            } else c.skip();
+        } while (c.eat(','));
+    }
+    return g;
+}
+
+GenomeData readFastaGenome(const std::string &path, const std::string &stem) {
+    std::ifstream f(path);
+    if (!f) throw IOException("Cannot read genome file " + path + ".");
+    GenomeData g;
+    g.id = stem;
+    g.name = stem;
+    std::string line;
+    while (std::getline(f, line)) {
+        while (!line.empty() && isspace((unsigned char)line.back())) line.pop_back();
+        if (line.empty()) continue;
+        if (line[0] == '>') g.contigs.emplace_back();
+        else if (!g.contigs.empty()) g.contigs.back() += line;
+    }
+    return g;
+}
+
+// GenomeSource.Type.create(dir): genomes of a source in sorted-name order
+std::vector<GenomeData> loadSource(const std::string &type, const std::string &dir) {
+    std::vector<std::string> files;
+    if (isDir(dir)) {
+        DIR *d = opendir(dir.c_str());
+        if (!d) throw IOException("Genome source \"" + dir + "\" is not readable.");
+        while (dirent *e = readdir(d)) files.push_back(e->d_name);
+        closedir(d);
+        std::sort(files.begin(), files.end());
+    } else {
+        files.push_back("");
+    }
+    std::vector<GenomeData> out;
+    for (auto &fn : files) {
+        std::string path = fn.empty() ? dir : dir + "/" + fn;
+        std::string base = fn.empty() ? dir.substr(dir.find_last_of('/') + 1) : fn;
+        size_t dot = base.find_last_of('.');
+        std::string ext = dot == std::string::npos ? "" : base.substr(dot);
+        std::string stem = dot == std::string::npos ? base : base.substr(0, dot);
+        if (type == "DIR") {
+            if (ext != ".gto") continue;
+            out.push_back(readGto(path));
+        } else {
+            if (ext != ".fa" && ext != ".fna" && ext != ".fasta") continue;
+            out.push_back(readFastaGenome(path, stem));
+        }
+    }
+    return out;
+}
+
+const std::vector<OptSpec> GENOME_OPTS = {
+    {{"--kmerSize", "-K", "--kmer"}, true, "DNA kmer size"},
+    {{"--maxDist", "-m", "--max", "--distance"}, true, "maximum acceptable distance for a neighboring genome"},
+    {{"--type", "-t"}, true, "genome source type (DIR = directory of GTO files; FASTA = directory of FASTA files)"},
+    {{"--output", "-o"}, true, "output file for report (if not STDOUT)"},
+    {{"--device"}, true, "CUDA device ordinal (additive option; default 0)"},
+    {{"--help", "-h"}, false, "display usage information"},
+    {{"--verbose", "-v"}, false, "show more detail on the log"},
+};
+
+int genomes(const std::vector<std::string> &args) {
+    Parsed p = parseOptions(GENOME_OPTS, args);
+    if (p.values.count("--help")) {
+        printUsage("genomes", GENOME_OPTS, "gtoDir gtoDir1 gtoDir2 ...");
+        return 0;
+    }
+    // setReporterDefaults (:75-79)
+    int kmerSize = p.values.count("--kmerSize") ? toInt("--kmerSize", p.values["--kmerSize"]) : 21;
+    double maxDist = p.values.count("--maxDist") ? toDouble("--maxDist", p.values["--maxDist"]) : 0.9;
+    std::string sourceType = p.values.count("--type") ? p.values["--type"] : "DIR";
+    int device = p.values.count("--device") ? toInt("--device", p.values["--device"]) : 0;
+    if (sourceType != "DIR" && sourceType != "FASTA")
+        throw ParseFailureException("\"" + sourceType + "\" is not a valid value for \"--type\"");
+    if (p.positional.size() < 1) throw ParseFailureException("Argument \"gtoDir\" is required");
+    if (p.positional.size() < 2) throw ParseFailureException("Argument \"gtoDir1 gtoDir2 ...\" is required");
+    // validateReporterParms (:82-116)
+    if (kmerSize < 4) throw ParseFailureException("Kmer size cannot be less than 4.");
+    logInfo("Chosen kmer size is " + std::to_string(kmerSize) + ".");
+    if (maxDist <= 0.0 || maxDist > 1.0) throw ParseFailureException("Maximum distance must be > 0 and <= 1.");
+    const std::string baseDir = p.positional[0];
+    if (!exists(baseDir)) throw IOException("Main genome source \"" + baseDir + "\" is not found.");
+    for (size_t i = 1; i < p.positional.size(); i++)
+        if (!exists(p.positional[i])) throw IOException("Genome source \"" + p.positional[i] + "\" is not found.");
+    std::ofstream ofile;
+    if (p.values.count("--output")) {
+        ofile.open(p.values["--output"]);
+        if (!ofile) throw IOException("Cannot open output file " + p.values["--output"] + ".");
+    }
+    std::ostream &writer = p.values.count("--output") ? (std::ostream &)ofile : std::cout;
+
+    KmerEngine engine(KmerType::DNA, kmerSize, device);
+    std::vector<SequenceKmers> mainKmers;
+    {
+        std::vector<GenomeData> base = loadSource(sourceType, baseDir);
+        logInfo("Loading " + std::to_string(base.size()) + " genomes from " + baseDir + ".");
+        for (auto &g : base) mainKmers.push_back(engine.genomeKmers(g.contigs, g.id, g.name));
+    }
+    // runReporter (:119-150): every genome of the other sources against all base genomes; the
+    // maxDist option is validated but, as in the reference, never applied to the output (:143-146)
+    writer << "genome1\tgenome2\tdistance\n";
+    std::vector<SequenceKmers> queries;
+    for (size_t i = 1; i < p.positional.size(); i++) {
+        logInfo("Loading genome directory " + p.positional[i] + ".");
+        for (auto &g : loadSource(sourceType, p.positional[i])) queries.push_back(engine.genomeKmers(g.contigs, g.id, g.name));
+    }
+    engine.build();
+    std::vector<uint32_t> q, r;
+    for (auto &s : queries) q.push_back(s.handle());
+    for (auto &s : mainKmers) r.push_back(s.handle());
+    std::vector<double> dist;
+    engine.queryVsRef(q, r, dist);
+    size_t compares = 0;
+    for (size_t qi = 0; qi < queries.size(); qi++)
+        for (size_t ri = 0; ri < mainKmers.size(); ri++, compares++)
+            writer << queries[qi].getGenomeId() << '\t' << mainKmers[ri].getGenomeId() << '\t'
+                   << javaDouble(dist[qi * mainKmers.size() + ri]) << '\n';
+    writer.flush();
+    logInfo(std::to_string(compares) + " comparisons output.");
+    return 0;
+}
+
+}  // namespace
+
+int main(int argc, char **argv) {
+    if (argc < 2) {
+        fprintf(stderr, "usage: gkd <fastaDist|genomes> [options]\n");
+        return 2;
+    }
+    std::string command = argv[1];
+    std::vector<std::string> rest(argv + 2, argv + argc);
+    try {
+        if (command == "fastaDist") return fastaDist(rest);
+        if (command == "genomes") return genomes(rest);
+        // App.java:104 -- IllegalArgumentException("Invalid command " + command)
+        fprintf(stderr, "Invalid command %s. (gkd implements the k-mer distance hot path: fastaDist, genomes)\n", command.c_str());
+        return 2;
+    } catch (const ParseFailureException &e) {
+        fprintf(stderr, "%s\n", e.what());  // BaseProcessor prints the message and the usage
+        printUsage(command, command == "genomes" ? GENOME_OPTS : FASTA_OPTS, command == "genomes" ? "gtoDir gtoDir1 gtoDir2 ..." : "");
+        return 1;
+    } catch (const IOException &e) {
+        fprintf(stderr, "%s\n", e.what());
+        return 1;
+    } catch (const std::exception &e) {
+        fprintf(stderr, "ERROR: %s\n", e.what());
+        return 3;
+    }
+}

@@ -1,0 +1,117 @@
+"""The `gkd` command mirrors the reference sub-commands: option names, validation messages
+(FastaDistanceProcessor.java:98-102, GenomeProcessor.java:84-98), headers and Double.toString text."""
+import json
+import os
+import random
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GKD = os.path.join(ROOT, "genome", "distance_b200", "gkd")
+
+
+def run(args, stdin=None):
+    p = subprocess.run([GKD] + args, input=stdin, capture_output=True, text=True, timeout=300)
+    return p.returncode, p.stdout, p.stderr
+
+
+def test_validation_messages_match_reference(tmp_path):
+    assert os.path.exists(GKD), "build first: python -c 'import __graft_entry__ as g; g.build()'"
+    rc, out, err = run(["fastaDist", "-K", "1"])
+    assert rc == 1 and err.startswith("Kmer size must be at least 2.")
+    rc, out, err = run(["fastaDist", "--batch", "0"])
+    assert rc == 1 and err.startswith("Batch size must be at least 1.")
+    rc, out, err = run(["fastaDist", "-i", str(tmp_path / "nope.fa")])
+    assert rc == 1 and "is not found or unreadable." in err
+    rc, out, err = run(["fastaDist", "--type", "BOGUS"])
+    assert rc == 1 and "is not a valid value for \"--type\"" in err
+    rc, out, err = run(["fastaDist", "--frobnicate"])
+    assert rc == 1 and "is not a valid option" in err
+    d = tmp_path / "g"
+    d.mkdir()
+    rc, out, err = run(["genomes", "-K", "3", str(d), str(d)])
+    assert rc == 1 and err.startswith("Kmer size cannot be less than 4.")
+    for bad in ("0", "1.5", "-0.2"):
+        rc, out, err = run(["genomes", "-m", bad, str(d), str(d)])
+        assert rc == 1 and "Maximum distance must be > 0 and <= 1." in err
+    rc, out, err = run(["genomes", str(tmp_path / "missing"), str(d)])
+    assert rc == 1 and err.strip().endswith("Main genome source \"%s\" is not found." % (tmp_path / "missing"))
+    rc, out, err = run(["genomes", str(d), str(tmp_path / "missing2")])
+    assert rc == 1 and "Genome source \"%s\" is not found." % (tmp_path / "missing2") in err
+    rc, out, err = run(["genomes", str(d)])
+    assert rc == 1 and "is required" in err
+    rc, out, err = run(["methodCorr"])
+    assert rc == 2 and "Invalid command methodCorr" in err
+
+
+def _rand(rng, n, alpha="acgt"):
+    return "".join(rng.choice(alpha) for _ in range(n))
+
+
+def _mut(rng, s, rate):
+    return "".join(rng.choice("acgt") if rng.random() < rate else c for c in s)
+
+
+@pytest.mark.gpu
+def test_fastadist_report_matches_oracle_text(orc, tmp_path):
+    rng = random.Random(3)
+    base = _rand(rng, 30000)
+    recs = [("g%03d" % i, "synthetic len=%d seed=%d" % (30000, i), _mut(rng, base, 0.01 * i)) for i in range(6)]
+    recs.append(("other", "", _rand(rng, 20000)))
+    fa = tmp_path / "in.fa"
+    with open(fa, "w") as f:
+        for label, comment, seq in recs:
+            f.write(">%s %s\n" % (label, comment))
+            for i in range(0, len(seq), 80):
+                f.write(seq[i:i + 80] + "\n")
+    want = ["seq1\tname1\tseq2\tname2\tdistance"]
+    sets = [orc.StrSet(s, 21) for _, _, s in recs]
+    for i in range(len(recs)):
+        for j in range(i + 1, len(recs)):
+            want.append("\t".join([recs[i][0], recs[i][1], recs[j][0], recs[j][1], orc.java_double(sets[i].distance(sets[j]))]))
+    rc, out, err = run(["fastaDist", "-i", str(fa)])
+    assert rc == 0, err
+    got = out.rstrip("\n").split("\n")
+    assert got[0] == want[0]
+    assert sorted(got[1:]) == sorted(want[1:])  # the reference's row order is nondeterministic
+    assert got[-1].endswith("\t1.0")
+    assert "7 sequences read from input." in err
+    # stdin + -o + protein type + explicit K
+    prot = ">p1 a\nMKVLAAGIVGLLLAQWERTY\n>p2 b\nMKVLAAGIVGLLLSQWERTY\n"
+    outp = tmp_path / "o.tbl"
+    rc, out, err = run(["fastaDist", "--type", "PROT", "-K", "8", "-o", str(outp)], stdin=prot)
+    assert rc == 0, err
+    assert outp.read_text() == "seq1\tname1\tseq2\tname2\tdistance\np1\ta\tp2\tb\t0.7\n"
+
+
+@pytest.mark.gpu
+def test_genomes_report_matches_oracle_text(orc, tmp_path):
+    rng = random.Random(8)
+    base = [_rand(rng, 20000), _rand(rng, 7000)]
+
+    def gto(dirp, gid, contigs):
+        obj = {"id": gid, "scientific_name": "Synthetic " + gid, "features": [{"id": "fig|1", "location": [["c1", 1, "+", 9]]}],
+               "contigs": [{"id": "c%d" % i, "dna": c, "genetic_code": 11} for i, c in enumerate(contigs)], "ncbi_taxonomy_id": 2}
+        with open(dirp / (gid + ".gto"), "w") as f:
+            json.dump(obj, f)
+
+    bdir, qdir = tmp_path / "base", tmp_path / "query"
+    bdir.mkdir()
+    qdir.mkdir()
+    refs = {"100.1": base, "100.2": [_mut(rng, c, 0.02) for c in base], "200.1": [_rand(rng, 15000)]}
+    qs = {"300.1": [_mut(rng, c, 0.05) for c in base], "300.2": [_rand(rng, 9000)]}
+    for gid, c in refs.items():
+        gto(bdir, gid, c)
+    for gid, c in qs.items():
+        gto(qdir, gid, c)
+    rsets = {g: orc.StrSet(c, 21) for g, c in refs.items()}
+    want = ["genome1\tgenome2\tdistance"]
+    for q in sorted(qs):
+        qset = orc.StrSet(qs[q], 21)
+        for r in sorted(refs):
+            want.append("%s\t%s\t%s" % (q, r, orc.java_double(qset.distance(rsets[r]))))
+    rc, out, err = run(["genomes", str(bdir), str(qdir)])
+    assert rc == 0, err
+    assert out.rstrip("\n").split("\n") == want  # deterministic order in this command
+    assert "6 comparisons output." in err
