@@ -497,7 +497,7 @@ int run_pairs(gkd_ctx *c, const HostPairs &hp, uint64_t *inter, double *dist) {
             seg = std::min<uint64_t>(seg, max_l);
         }
     }
-    seg = std::max<uint64_t>(seg, ISECT_W);
+    seg = std::max<uint64_t>(seg, (uint64_t)intersect_min_segment());
     seg = std::min<uint64_t>(seg, 0xFFFF0000ull);
     const uint32_t max_segs = (uint32_t)((max_l + seg - 1) / seg);
 

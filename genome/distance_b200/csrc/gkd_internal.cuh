@@ -21,19 +21,14 @@ constexpr uint64_t KEY_SENTINEL = 0xFFFFFFFFFFFFFFFFull;
 
 // Intersect kernel geometry.  A set in HBM is `n` sorted keys followed by sentinel keys up to
 // set_padded(n): the kernel stages fixed ISECT_BLK-key blocks with TMA bulk copies and relies on the
-// sentinels instead of bounds checks.
+// sentinels instead of bounds checks.  ISECT_W_MAX bounds the per-round window of every kernel
+// configuration (threads x keys-per-thread), so one padding rule serves them all.
 constexpr int ISECT_BLK = 512;       // keys per TMA bulk copy (4 KiB)
-constexpr int ISECT_NBLK = 8;        // ring slots per input
-constexpr int ISECT_CAP = ISECT_BLK * ISECT_NBLK;  // 4096 keys = 32 KiB per input ring
-constexpr int ISECT_THREADS = 256;
-constexpr int ISECT_VT = 8;                        // merged keys per thread per round
-constexpr int ISECT_W = ISECT_THREADS * ISECT_VT;  // 2048 merged keys per round
-static_assert(ISECT_W + ISECT_BLK <= ISECT_CAP, "ring must hold a full round window");
-static_assert((ISECT_CAP & (ISECT_CAP - 1)) == 0, "ring capacity must be a power of two");
+constexpr int ISECT_W_MAX = 4096;    // largest per-round merge window of any configuration
 
 __host__ __device__ inline uint64_t set_padded(uint64_t n) {
     // room for the window [i, i+W] at i == n, rounded to whole blocks
-    return ((n + ISECT_W + 1 + ISECT_BLK - 1) / ISECT_BLK) * (uint64_t)ISECT_BLK;
+    return ((n + ISECT_W_MAX + 1 + ISECT_BLK - 1) / ISECT_BLK) * (uint64_t)ISECT_BLK;
 }
 
 // Packed residue streams.  A genome is one stream: its contigs joined by one separator position.
@@ -121,6 +116,7 @@ cudaError_t launch_fill_u64(uint64_t *dst, uint64_t n, uint64_t value, cudaStrea
 cudaError_t intersect_configure();
 cudaError_t launch_intersect(const SetDesc *sets, PairSource src, int use_pal, uint32_t seg_keys, uint32_t max_segs,
                              uint32_t *counts, unsigned long long *work_counter, int n_sms, cudaStream_t s);
+int intersect_min_segment();  // smallest useful merge-path segment (one full round of the active config)
 cudaError_t launch_epilogue(const SetDesc *sets, PairSource src, const uint32_t *counts, const uint32_t *pal_counts,
                             int both_strands, uint64_t *inter, double *dist, cudaStream_t s);
 // synthetic data

@@ -10,25 +10,28 @@
 //   (query, base) pair (GenomeProcessor.java:140-146).
 //
 // Kernel 4 design (B200):
-//   * persistent CTAs (3 per SM, 256 threads) pull work items (pair, merge-path segment) from one
-//     global counter; pairs are enumerated row-major so CTAs resident at the same time mostly share
-//     the row genome and it is served from the 126 MB L2 instead of HBM;
-//   * each input is streamed through a 32 KiB shared-memory ring filled by TMA bulk copies
-//     (cp.async.bulk, 4 KiB blocks, one mbarrier per ring slot); sets carry a sentinel tail so no
-//     bounds checks are needed; the ring is refilled as soon as a block is consumed, which keeps
-//     about two rounds of loads in flight per CTA;
-//   * a round merges W = 2048 keys: every thread finds its merge-path split in shared memory and
-//     then merges 8 keys serially, counting equal heads; the last thread's end point advances the
-//     stream heads;
+//   * persistent CTAs pull work items (pair, merge-path segment) from one global counter; pairs are
+//     enumerated row-major so CTAs resident at the same time mostly share the row genome, which is
+//     then served from the 126 MB L2 instead of HBM (measured DRAM traffic ~0.47x algorithmic);
+//   * each input is streamed through a shared-memory ring filled by TMA bulk copies
+//     (cp.async.bulk, 4 KiB blocks, one mbarrier per ring slot, thread 0 issues);
+//     sets carry a sentinel tail so the merge needs no bounds checks; a slot is refilled as soon
+//     as its block is consumed, which keeps 0.3-0.75 windows of loads in flight per CTA;
+//   * a round merges W = THREADS x VT keys: every thread finds its merge-path split in shared
+//     memory (byte-address binary search) and then merges VT keys serially, counting equal heads;
+//     the last thread's end point advances the stream heads;
 //   * segment starts inside a pair are found by a warp-cooperative 32-ary merge-path search on
 //     global memory (__ballot_sync / __popc select the sub-range);
 //   * per-warp shuffle reduction, one atomicAdd per warp per item.
-// Bound: HBM (or L2 when the row set is resident).  Algorithmic bytes: 8 * (|A| + |B|) per pair.
+// Bound: nominally HBM; measured limiter is the shared-memory pipe + issue slots (see profiles/).
+// Algorithmic bytes: 8 * (|A| + |B|) per pair.
+#include <cstdlib>
+
 #include "gkd_internal.cuh"
 
 namespace gkd {
 
-// ---- mbarrier / TMA wrappers ------------------------------------------------------------------------
+// ---- mbarrier / TMA / shared-memory wrappers --------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
@@ -58,15 +61,11 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         if (!done && ++spins > (1u << 24)) __trap();  // a lost copy must not hang the GPU
     }
 }
-
-struct __align__(128) IsectSmem {
-    uint64_t ring[2][ISECT_CAP];
-    uint64_t bar[2][ISECT_NBLK];
-    unsigned long long item[2];
-    uint32_t ida[2], idb[2];
-    uint32_t heads[2][2];
-    uint32_t start[2];
-};
+__device__ __forceinline__ uint64_t lds64(uint32_t addr) {
+    uint64_t v;
+    asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(addr));
+    return v;
+}
 
 // decode pair index t of this call into set ids
 __device__ __forceinline__ void decode_pair(const PairSource &src, uint64_t t, uint32_t &ida, uint32_t &idb) {
@@ -79,56 +78,6 @@ __device__ __forceinline__ void decode_pair(const PairSource &src, uint64_t t, u
         ida = src.a[t];
         idb = src.b[t];
     }
-}
-
-// One input stream: a ring of ISECT_NBLK blocks of a sentinel-padded sorted key array.
-struct Stream {
-    const uint64_t *keys;  // global base of the set
-    uint32_t head;         // next unconsumed key
-    uint32_t g0;           // first block of this item
-    uint32_t v0;           // virtual (CTA-lifetime) block counter at g0: slot = v % NBLK, parity = (v / NBLK) & 1
-    uint32_t issued;       // next block to request
-    uint32_t ready;        // blocks < ready are known to have landed
-    uint32_t limit;        // one past the last block this item can touch
-    uint32_t shift;        // ring index of key position p is (p + shift) & (CAP - 1)
-};
-
-__device__ __forceinline__ void stream_begin(Stream &s, const uint64_t *keys, uint32_t n, uint32_t head0,
-                                             uint32_t max_consume, uint32_t vnext) {
-    s.keys = keys;
-    s.head = head0;
-    s.g0 = head0 / ISECT_BLK;
-    s.v0 = vnext;
-    s.issued = s.g0;
-    s.ready = s.g0;
-    uint64_t last_pos = (uint64_t)head0 + max_consume;
-    if (last_pos > n) last_pos = n;
-    s.limit = (uint32_t)((last_pos + ISECT_W) / ISECT_BLK) + 1;
-    s.shift = (s.v0 - s.g0) * (uint32_t)ISECT_BLK;
-}
-
-// request every block whose ring slot is free (thread 0 issues; all threads track the counter)
-__device__ __forceinline__ void stream_issue(Stream &s, uint32_t ring_addr, uint32_t bar_addr) {
-    uint32_t upto = s.head / ISECT_BLK + ISECT_NBLK;
-    if (upto > s.limit) upto = s.limit;
-    if (threadIdx.x == 0) {
-        for (uint32_t g = s.issued; g < upto; g++) {
-            uint32_t slot = (s.v0 + (g - s.g0)) % ISECT_NBLK;
-            uint32_t bar = bar_addr + slot * 8;
-            mbar_expect_tx(bar, ISECT_BLK * 8);
-            tma_load_1d(ring_addr + slot * (ISECT_BLK * 8), s.keys + (size_t)g * ISECT_BLK, ISECT_BLK * 8, bar);
-        }
-    }
-    if (upto > s.issued) s.issued = upto;
-}
-
-// block until blocks [ready, upto) have landed
-__device__ __forceinline__ void stream_wait(Stream &s, uint32_t upto, uint32_t bar_addr) {
-    for (uint32_t g = s.ready; g < upto; g++) {
-        uint32_t v = s.v0 + (g - s.g0);
-        mbar_wait(bar_addr + (v % ISECT_NBLK) * 8, (v / ISECT_NBLK) & 1u);
-    }
-    if (upto > s.ready) s.ready = upto;
 }
 
 // Merge-path split of diagonal d over two global arrays (A first on ties): the number of A keys
@@ -155,19 +104,149 @@ __device__ __forceinline__ uint32_t diag_search_global(const uint64_t *__restric
     return lo;
 }
 
-__global__ void __launch_bounds__(ISECT_THREADS, 3)
+// Kernel configuration: THREADS x VT keys per round, ring of NBLK blocks per input.
+template <int THREADS_, int VT_, int NBLK_, int CTAS_>
+struct IsectCfg {
+    static constexpr int THREADS = THREADS_, VT = VT_, NBLK = NBLK_, CTAS = CTAS_;
+    static constexpr int W = THREADS * VT;
+    static constexpr int CAP = NBLK * ISECT_BLK;         // keys per ring
+    static constexpr uint32_t CAPB = (uint32_t)CAP * 8u;  // bytes per ring
+    static constexpr uint32_t BAR_OFF = 2u * CAPB;
+    static constexpr uint32_t MISC_OFF = BAR_OFF + 2u * NBLK * 8u;
+    static constexpr uint32_t SMEM = MISC_OFF + 64u;
+    static_assert(W <= ISECT_W_MAX, "sets are padded for windows up to ISECT_W_MAX keys");
+    static_assert(CAP >= W + ISECT_BLK, "ring must hold a full round window at any alignment");
+    static_assert((size_t)SMEM * CTAS <= 227u * 1024u - 1024u * CTAS, "does not fit the SM");
+};
+
+struct IsectMisc {  // broadcast slots (double-buffered by item / round parity)
+    unsigned long long item[2];
+    uint32_t ida[2], idb[2];
+    uint32_t heads[2];
+    uint32_t start[2];
+};
+
+// One input stream: a ring of NBLK blocks of a sentinel-padded sorted key array.  Every thread keeps
+// an identical copy of this state; only thread 0 issues copies.
+struct Stream {
+    const uint64_t *keys;
+    uint32_t head;    // next unconsumed key (set position)
+    uint32_t hidx;    // ring index (keys) of `head`
+    uint32_t g0, v0;  // first block of this item and its CTA-lifetime virtual block number
+    uint32_t issued;  // next block (set numbering) to request
+    uint32_t ready;   // blocks < ready are known to have landed
+    uint32_t limit;   // one past the last block this item can touch
+};
+
+template <class C>
+__device__ __forceinline__ void stream_begin(Stream &s, const uint64_t *keys, uint32_t n, uint32_t head0,
+                                             uint32_t max_consume, uint32_t vnext) {
+    s.keys = keys;
+    s.head = head0;
+    s.g0 = head0 / ISECT_BLK;
+    s.v0 = vnext;
+    s.hidx = (vnext % C::NBLK) * ISECT_BLK + head0 % ISECT_BLK;
+    s.issued = s.g0;
+    s.ready = s.g0;
+    uint64_t last_pos = (uint64_t)head0 + max_consume;
+    if (last_pos > n) last_pos = n;
+    s.limit = (uint32_t)((last_pos + C::W) / ISECT_BLK) + 1;
+}
+
+// request every block whose ring slot is free
+template <class C>
+__device__ __forceinline__ void stream_issue(Stream &s, uint32_t ring_addr, uint32_t bar_addr) {
+    uint32_t upto = s.head / ISECT_BLK + C::NBLK;
+    if (upto > s.limit) upto = s.limit;
+    if (threadIdx.x == 0) {
+        for (uint32_t g = s.issued; g < upto; g++) {
+            uint32_t slot = (s.v0 + (g - s.g0)) % C::NBLK;
+            uint32_t bar = bar_addr + slot * 8;
+            mbar_expect_tx(bar, ISECT_BLK * 8);
+            tma_load_1d(ring_addr + slot * (ISECT_BLK * 8), s.keys + (size_t)g * ISECT_BLK, ISECT_BLK * 8, bar);
+        }
+    }
+    if (upto > s.issued) s.issued = upto;
+}
+
+// every thread blocks until blocks [ready, upto) have landed (observing the mbarrier phase is what
+// makes the async-proxy writes visible to that thread)
+template <class C>
+__device__ __forceinline__ void stream_wait(Stream &s, uint32_t upto, uint32_t bar_addr) {
+    for (uint32_t g = s.ready; g < upto; g++) {
+        uint32_t v = s.v0 + (g - s.g0);
+        mbar_wait(bar_addr + (v % C::NBLK) * 8, (v / C::NBLK) & 1u);
+    }
+    if (upto > s.ready) s.ready = upto;
+}
+
+// One merge round over r <= W keys.  FULL rounds (r == W) run the branch-free VT-step merge.
+template <class C, bool FULL>
+__device__ __forceinline__ uint32_t merge_round(uint32_t hA, uint32_t hB, uint32_t rA0, uint32_t rB0, uint32_t r,
+                                                uint32_t &cnt, bool &is_last) {
+    constexpr uint32_t CAPB = C::CAPB;
+    const uint32_t rA1 = rA0 + CAPB, rB1 = rB0 + CAPB;
+    uint32_t d = (uint32_t)threadIdx.x * C::VT;
+    if (!FULL && d > r) d = r;
+    // merge-path split of this thread's diagonal inside the window (A first on ties)
+    uint32_t lo = 0, hi = d;
+    const uint32_t bBase = hB + (d - 1) * 8u;  // address of B[d-1] before wrapping (unused when d == 0)
+    while (lo < hi) {
+        uint32_t mid = (lo + hi) >> 1;
+        uint32_t aa = hA + mid * 8u;
+        if (aa >= rA1) aa -= CAPB;
+        uint32_t bb = bBase - mid * 8u;
+        if (bb >= rB1) bb -= CAPB;
+        if (lds64(aa) <= lds64(bb)) lo = mid + 1;
+        else hi = mid;
+    }
+    uint32_t pa = hA + lo * 8u;
+    if (pa >= rA1) pa -= CAPB;
+    uint32_t pb = hB + (d - lo) * 8u;
+    if (pb >= rB1) pb -= CAPB;
+    const uint32_t pa0 = pa;
+    uint64_t a = lds64(pa), b = lds64(pb);
+    uint32_t steps = C::VT;
+    if (!FULL) {
+        steps = r - d;
+        if (steps > (uint32_t)C::VT) steps = C::VT;
+    }
+#pragma unroll
+    for (int s = 0; s < C::VT; s++) {
+        if (FULL || (uint32_t)s < steps) {
+            const bool take_a = a <= b;
+            cnt += (a == b) ? 1u : 0u;  // counted once, when the A copy is consumed
+            if (take_a) {
+                pa += 8u;
+                if (pa == rA1) pa = rA0;
+                a = lds64(pa);
+            } else {
+                pb += 8u;
+                if (pb == rB1) pb = rB0;
+                b = lds64(pb);
+            }
+        }
+    }
+    // the thread that ends exactly on the round's last diagonal reports how many A keys were used
+    is_last = FULL ? (threadIdx.x == C::THREADS - 1) : (d < r && d + C::VT >= r);
+    uint32_t usedA = (pa >= pa0 ? pa - pa0 : pa + CAPB - pa0) / 8u;
+    return lo + usedA;
+}
+
+template <class C>
+__global__ void __launch_bounds__(C::THREADS, C::CTAS)
     k_intersect(const SetDesc *__restrict__ sets, PairSource src, int use_pal, uint32_t seg_keys, uint32_t max_segs,
                 uint32_t *__restrict__ counts, unsigned long long *__restrict__ work_counter) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    IsectSmem &sm = *reinterpret_cast<IsectSmem *>(smem_raw);
+    const uint32_t smem0 = smem_u32(smem_raw);
+    const uint32_t ringA = smem0, ringB = smem0 + C::CAPB;
+    const uint32_t barA = smem0 + C::BAR_OFF, barB = barA + C::NBLK * 8u;
+    IsectMisc &misc = *reinterpret_cast<IsectMisc *>(smem_raw + C::MISC_OFF);
     const int tid = threadIdx.x;
     const int lane = tid & 31;
-    const uint32_t ringA = smem_u32(&sm.ring[0][0]), ringB = smem_u32(&sm.ring[1][0]);
-    const uint32_t barA = smem_u32(&sm.bar[0][0]), barB = smem_u32(&sm.bar[1][0]);
-    constexpr uint32_t M = ISECT_CAP - 1;
 
     if (tid == 0) {
-        for (int s = 0; s < ISECT_NBLK; s++) {
+        for (int s = 0; s < C::NBLK; s++) {
             mbar_init(barA + s * 8, 1);
             mbar_init(barB + s * 8, 1);
         }
@@ -178,25 +257,25 @@ __global__ void __launch_bounds__(ISECT_THREADS, 3)
     const uint64_t total_items = src.count * (uint64_t)max_segs;
     uint32_t vnextA = 0, vnextB = 0;  // CTA-lifetime virtual block counters (identical in every thread)
     uint32_t it = 0;                  // item parity for the broadcast slots
-    uint32_t round_parity = 0;
+    uint32_t rp = 0;                  // round parity
 
     for (;; it ^= 1u) {
         if (tid == 0) {
             unsigned long long item = atomicAdd(work_counter, 1ull);
-            sm.item[it] = item;
+            misc.item[it] = item;
             if (item < total_items) {
                 uint32_t a, b;
                 decode_pair(src, item / max_segs, a, b);
-                sm.ida[it] = a;
-                sm.idb[it] = b;
+                misc.ida[it] = a;
+                misc.idb[it] = b;
             }
         }
         __syncthreads();
-        const uint64_t item = sm.item[it];
+        const uint64_t item = misc.item[it];
         if (item >= total_items) break;
         const uint64_t pair = item / max_segs;
         const uint32_t seg = (uint32_t)(item % max_segs);
-        const SetDesc SA = sets[sm.ida[it]], SB = sets[sm.idb[it]];
+        const SetDesc SA = sets[misc.ida[it]], SB = sets[misc.idb[it]];
         const uint64_t *keysA = use_pal ? SA.pal_keys : SA.keys;
         const uint64_t *keysB = use_pal ? SB.pal_keys : SB.keys;
         const uint32_t nA = use_pal ? SA.n_pal : SA.n;
@@ -212,89 +291,102 @@ __global__ void __launch_bounds__(ISECT_THREADS, 3)
         if (seg != 0) {
             if (tid < 32) {
                 uint32_t s = diag_search_global(keysA, nA, keysB, nB, d0);
-                if (lane == 0) sm.start[it] = s;
+                if (lane == 0) misc.start[it] = s;
             }
             __syncthreads();
-            i0 = sm.start[it];
+            i0 = misc.start[it];
             j0 = (uint32_t)(d0 - i0);
         }
 
         Stream sa, sb;
-        stream_begin(sa, keysA, nA, i0, rem, vnextA);
-        stream_begin(sb, keysB, nB, j0, rem, vnextB);
+        stream_begin<C>(sa, keysA, nA, i0, rem, vnextA);
+        stream_begin<C>(sb, keysB, nB, j0, rem, vnextB);
         uint32_t cnt = 0;
 
         while (rem > 0) {
-            const uint32_t r = rem < (uint32_t)ISECT_W ? rem : (uint32_t)ISECT_W;
-            stream_issue(sa, ringA, barA);
-            stream_issue(sb, ringB, barB);
-            {
-                uint32_t needA = (sa.head + ISECT_W) / ISECT_BLK + 1;
-                uint32_t needB = (sb.head + ISECT_W) / ISECT_BLK + 1;
-                stream_wait(sa, needA < sa.limit ? needA : sa.limit, barA);
-                stream_wait(sb, needB < sb.limit ? needB : sb.limit, barB);
-            }
-            const uint32_t baseA = sa.head + sa.shift, baseB = sb.head + sb.shift;
-            // merge-path split of this thread's diagonal inside the window (A first on ties)
-            uint32_t d = (uint32_t)tid * ISECT_VT;
-            if (d > r) d = r;
-            uint32_t lo = 0, hi = d;
-            while (lo < hi) {
-                uint32_t mid = (lo + hi) >> 1;
-                uint64_t a = sm.ring[0][(baseA + mid) & M];
-                uint64_t b = sm.ring[1][(baseB + d - 1 - mid) & M];
-                if (a <= b) lo = mid + 1;
-                else hi = mid;
-            }
-            uint32_t ia = lo, ib = d - lo;
-            uint32_t steps = r - d;
-            if (steps > (uint32_t)ISECT_VT) steps = ISECT_VT;
-            uint32_t pa = (baseA + ia) & M, pb = (baseB + ib) & M;
-            uint64_t a = sm.ring[0][pa], b = sm.ring[1][pb];
-#pragma unroll
-            for (int s = 0; s < ISECT_VT; s++) {
-                if ((uint32_t)s < steps) {
-                    bool take_a = a <= b;
-                    cnt += (a == b) ? 1u : 0u;  // counted once, when the A copy is consumed
-                    if (take_a) {
-                        pa = (pa + 1) & M;
-                        ia++;
-                        a = sm.ring[0][pa];
-                    } else {
-                        pb = (pb + 1) & M;
-                        ib++;
-                        b = sm.ring[1][pb];
-                    }
-                }
-            }
-            if (d < r && d + ISECT_VT >= r) {  // this thread ends exactly on the round's last diagonal
-                sm.heads[round_parity][0] = ia;
-                sm.heads[round_parity][1] = ib;
-            }
-            __syncthreads();
-            sa.head += sm.heads[round_parity][0];
-            sb.head += sm.heads[round_parity][1];
+            const uint32_t r = rem < (uint32_t)C::W ? rem : (uint32_t)C::W;
+            stream_issue<C>(sa, ringA, barA);
+            stream_issue<C>(sb, ringB, barB);
+            stream_wait<C>(sa, (sa.head + C::W) / ISECT_BLK + 1, barA);
+            stream_wait<C>(sb, (sb.head + C::W) / ISECT_BLK + 1, barB);
+            const uint32_t hA = ringA + sa.hidx * 8u, hB = ringB + sb.hidx * 8u;
+            bool is_last;
+            uint32_t endA;
+            if (r == (uint32_t)C::W) endA = merge_round<C, true>(hA, hB, ringA, ringB, r, cnt, is_last);
+            else endA = merge_round<C, false>(hA, hB, ringA, ringB, r, cnt, is_last);
+            if (is_last) misc.heads[rp] = endA;
+            __syncthreads();  // window fully consumed: heads may move and freed slots may be refilled
+            const uint32_t usedA = misc.heads[rp], usedB = r - usedA;
+            sa.head += usedA;
+            sb.head += usedB;
+            sa.hidx += usedA;
+            if (sa.hidx >= (uint32_t)C::CAP) sa.hidx -= C::CAP;
+            sb.hidx += usedB;
+            if (sb.hidx >= (uint32_t)C::CAP) sb.hidx -= C::CAP;
             rem -= r;
-            round_parity ^= 1u;
+            rp ^= 1u;
         }
         // drain copies that were requested but never needed, so the slots can be re-armed
-        stream_wait(sa, sa.issued, barA);
-        stream_wait(sb, sb.issued, barB);
+        stream_wait<C>(sa, sa.issued, barA);
+        stream_wait<C>(sb, sb.issued, barB);
         vnextA += sa.issued - sa.g0;
         vnextB += sb.issued - sb.g0;
 
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
         if (lane == 0 && cnt) atomicAdd(&counts[pair], cnt);
-        __syncthreads();  // every thread is done with the ring before the next item re-arms it
+        __syncthreads();  // every thread has drained before thread 0 re-arms slots for the next item
     }
 }
 
-static int g_isect_smem = 0;
+// Configurations tried on B200 (see profiles/): index selected with GKD_ISECT_CFG.  VT is odd on
+// purpose: lane l starts about l*VT/2 keys into each ring, and with an even VT that stride maps
+// whole half-warps onto 2-4 shared-memory banks (measured 62% of LDS wavefronts were replays).
+using Cfg0 = IsectCfg<256, 15, 12, 2>;  // W=3840, 48 KiB rings, 2 CTAs/SM (16 warps)
+using Cfg1 = IsectCfg<192, 15, 9, 3>;   // W=2880, 36 KiB rings, 3 CTAs/SM (18 warps)
+using Cfg2 = IsectCfg<192, 17, 9, 3>;   // W=3264
+using Cfg3 = IsectCfg<256, 9, 8, 3>;    // W=2304, 32 KiB rings, 3 CTAs/SM (24 warps)
+using Cfg4 = IsectCfg<128, 17, 8, 3>;   // W=2176, 32 KiB rings, 3 CTAs/SM (12 warps)
+using Cfg5 = IsectCfg<192, 16, 9, 3>;   // even-VT control
+constexpr int N_CFG = 6;
+constexpr int DEFAULT_CFG = 1;
+
+static int g_cfg = DEFAULT_CFG;
+
+static int pick_cfg() {
+    const char *e = getenv("GKD_ISECT_CFG");
+    int c = e ? atoi(e) : DEFAULT_CFG;
+    return (c < 0 || c >= N_CFG) ? DEFAULT_CFG : c;
+}
+
+#define GKD_FOR_EACH_CFG(X) X(0, Cfg0) X(1, Cfg1) X(2, Cfg2) X(3, Cfg3) X(4, Cfg4) X(5, Cfg5)
 
 cudaError_t intersect_configure() {
-    g_isect_smem = (int)sizeof(IsectSmem);
-    return cudaFuncSetAttribute(k_intersect, cudaFuncAttributeMaxDynamicSharedMemorySize, g_isect_smem);
+    g_cfg = pick_cfg();
+    cudaError_t e;
+#define X(i, C) \
+    if ((e = cudaFuncSetAttribute(k_intersect<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM))) return e;
+    GKD_FOR_EACH_CFG(X)
+#undef X
+    return cudaSuccess;
+}
+
+int intersect_min_segment() {
+#define X(i, C) \
+    if (g_cfg == i) return C::W;
+    GKD_FOR_EACH_CFG(X)
+#undef X
+    return ISECT_W_MAX;
+}
+
+template <class C>
+static cudaError_t launch_cfg(const SetDesc *sets, PairSource src, int use_pal, uint32_t seg_keys, uint32_t max_segs,
+                              uint32_t *counts, unsigned long long *work_counter, int n_sms, cudaStream_t s) {
+    uint64_t items = src.count * (uint64_t)max_segs;
+    uint64_t grid = (uint64_t)n_sms * C::CTAS;  // persistent: every SM holds CTAS resident CTAs
+    if (grid > items) grid = items;
+    k_intersect<C><<<(unsigned)grid, C::THREADS, C::SMEM, s>>>(sets, src, use_pal, seg_keys, max_segs, counts, work_counter);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_intersect(const SetDesc *sets, PairSource src, int use_pal, uint32_t seg_keys, uint32_t max_segs,
@@ -302,12 +394,11 @@ cudaError_t launch_intersect(const SetDesc *sets, PairSource src, int use_pal, u
     if (src.count == 0) return cudaSuccess;
     cudaError_t e = cudaMemsetAsync(work_counter, 0, sizeof(unsigned long long), s);
     if (e != cudaSuccess) return e;
-    uint64_t items = src.count * (uint64_t)max_segs;
-    uint64_t grid = (uint64_t)n_sms * 3;  // persistent: 3 resident CTAs per SM
-    if (grid > items) grid = items;
-    k_intersect<<<(unsigned)grid, ISECT_THREADS, g_isect_smem, s>>>(sets, src, use_pal, seg_keys, max_segs, counts,
-                                                                    work_counter);
-    return cudaGetLastError();
+#define X(i, C) \
+    if (g_cfg == i) return launch_cfg<C>(sets, src, use_pal, seg_keys, max_segs, counts, work_counter, n_sms, s);
+    GKD_FOR_EACH_CFG(X)
+#undef X
+    return cudaErrorInvalidValue;
 }
 
 // ---- kernel 5: distance epilogue ----------------------------------------------------------------------
