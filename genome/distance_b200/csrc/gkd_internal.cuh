@@ -27,8 +27,8 @@ constexpr int ISECT_BLK = 512;       // keys per TMA bulk copy (4 KiB)
 constexpr int ISECT_W_MAX = 4096;    // largest per-round merge window of any configuration
 
 __host__ __device__ inline uint64_t set_padded(uint64_t n) {
-    // room for the window [i, i+W] at i == n, rounded to whole blocks
-    return ((n + ISECT_W_MAX + 1 + ISECT_BLK - 1) / ISECT_BLK) * (uint64_t)ISECT_BLK;
+    // room for the window [i, i+W+1] at i == n, rounded to whole blocks
+    return ((n + ISECT_W_MAX + 2 + ISECT_BLK - 1) / ISECT_BLK) * (uint64_t)ISECT_BLK;
 }
 
 // Packed residue streams.  A genome is one stream: its contigs joined by one separator position.

@@ -46,9 +46,19 @@ __device__ __forceinline__ void tma_load_1d(uint32_t dst, const void *src, uint3
                  : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    uint32_t done = 0;
+    uint32_t done;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (done) return;
     uint32_t spins = 0;
-    while (!done) {
+    do {
         asm volatile(
             "{\n"
             ".reg .pred p;\n"
@@ -58,8 +68,8 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
             : "=r"(done)
             : "r"(bar), "r"(parity)
             : "memory");
-        if (!done && ++spins > (1u << 24)) __trap();  // a lost copy must not hang the GPU
-    }
+        if (++spins > (1u << 24)) __trap();  // a lost copy must not hang the GPU
+    } while (!done);
 }
 __device__ __forceinline__ uint64_t lds64(uint32_t addr) {
     uint64_t v;
@@ -115,7 +125,8 @@ struct IsectCfg {
     static constexpr uint32_t MISC_OFF = BAR_OFF + 2u * NBLK * 8u;
     static constexpr uint32_t SMEM = MISC_OFF + 64u;
     static_assert(W <= ISECT_W_MAX, "sets are padded for windows up to ISECT_W_MAX keys");
-    static_assert(CAP >= W + ISECT_BLK, "ring must hold a full round window at any alignment");
+    static constexpr int WIN = W;  // furthest key index a round may read, relative to the head
+    static_assert(CAP >= WIN + 1 + ISECT_BLK, "ring must hold a full round window at any alignment");
     static_assert((size_t)SMEM * CTAS <= 227u * 1024u - 1024u * CTAS, "does not fit the SM");
 };
 
@@ -135,6 +146,8 @@ struct Stream {
     uint32_t g0, v0;  // first block of this item and its CTA-lifetime virtual block number
     uint32_t issued;  // next block (set numbering) to request
     uint32_t ready;   // blocks < ready are known to have landed
+    uint32_t rbar;    // shared address of the mbarrier of block `ready`
+    uint32_t rpar;    // phase parity to wait for on that barrier
     uint32_t limit;   // one past the last block this item can touch
 };
 
@@ -148,9 +161,11 @@ __device__ __forceinline__ void stream_begin(Stream &s, const uint64_t *keys, ui
     s.hidx = (vnext % C::NBLK) * ISECT_BLK + head0 % ISECT_BLK;
     s.issued = s.g0;
     s.ready = s.g0;
+    s.rbar = (vnext % C::NBLK) * 8u;  // offset; the array base is added at the wait
+    s.rpar = (vnext / C::NBLK) & 1u;
     uint64_t last_pos = (uint64_t)head0 + max_consume;
     if (last_pos > n) last_pos = n;
-    s.limit = (uint32_t)((last_pos + C::W) / ISECT_BLK) + 1;
+    s.limit = (uint32_t)((last_pos + C::WIN) / ISECT_BLK) + 1;
 }
 
 // request every block whose ring slot is free
@@ -173,11 +188,15 @@ __device__ __forceinline__ void stream_issue(Stream &s, uint32_t ring_addr, uint
 // makes the async-proxy writes visible to that thread)
 template <class C>
 __device__ __forceinline__ void stream_wait(Stream &s, uint32_t upto, uint32_t bar_addr) {
-    for (uint32_t g = s.ready; g < upto; g++) {
-        uint32_t v = s.v0 + (g - s.g0);
-        mbar_wait(bar_addr + (v % C::NBLK) * 8, (v / C::NBLK) & 1u);
+    while (s.ready < upto) {
+        mbar_wait(bar_addr + s.rbar, s.rpar);
+        s.ready++;
+        s.rbar += 8u;
+        if (s.rbar == C::NBLK * 8u) {
+            s.rbar = 0;
+            s.rpar ^= 1u;
+        }
     }
-    if (upto > s.ready) s.ready = upto;
 }
 
 // One merge round over r <= W keys.  FULL rounds (r == W) run the branch-free VT-step merge.
@@ -307,8 +326,8 @@ __global__ void __launch_bounds__(C::THREADS, C::CTAS)
             const uint32_t r = rem < (uint32_t)C::W ? rem : (uint32_t)C::W;
             stream_issue<C>(sa, ringA, barA);
             stream_issue<C>(sb, ringB, barB);
-            stream_wait<C>(sa, (sa.head + C::W) / ISECT_BLK + 1, barA);
-            stream_wait<C>(sb, (sb.head + C::W) / ISECT_BLK + 1, barB);
+            stream_wait<C>(sa, (sa.head + C::WIN) / ISECT_BLK + 1, barA);
+            stream_wait<C>(sb, (sb.head + C::WIN) / ISECT_BLK + 1, barB);
             const uint32_t hA = ringA + sa.hidx * 8u, hB = ringB + sb.hidx * 8u;
             bool is_last;
             uint32_t endA;
@@ -342,14 +361,14 @@ __global__ void __launch_bounds__(C::THREADS, C::CTAS)
 // Configurations tried on B200 (see profiles/): index selected with GKD_ISECT_CFG.  VT is odd on
 // purpose: lane l starts about l*VT/2 keys into each ring, and with an even VT that stride maps
 // whole half-warps onto 2-4 shared-memory banks (measured 62% of LDS wavefronts were replays).
-using Cfg0 = IsectCfg<256, 15, 12, 2>;  // W=3840, 48 KiB rings, 2 CTAs/SM (16 warps)
-using Cfg1 = IsectCfg<192, 15, 9, 3>;   // W=2880, 36 KiB rings, 3 CTAs/SM (18 warps)
-using Cfg2 = IsectCfg<192, 17, 9, 3>;   // W=3264
-using Cfg3 = IsectCfg<256, 9, 8, 3>;    // W=2304, 32 KiB rings, 3 CTAs/SM (24 warps)
-using Cfg4 = IsectCfg<128, 17, 8, 3>;   // W=2176, 32 KiB rings, 3 CTAs/SM (12 warps)
-using Cfg5 = IsectCfg<192, 16, 9, 3>;   // even-VT control
+using Cfg0 = IsectCfg<192, 17, 9, 3>;   // W=3264, 36 KiB rings, 3 CTAs/SM (18 warps)
+using Cfg1 = IsectCfg<160, 21, 9, 3>;   // W=3360 (15 warps)
+using Cfg2 = IsectCfg<128, 25, 9, 3>;   // W=3200 (12 warps)
+using Cfg3 = IsectCfg<224, 15, 9, 3>;   // W=3360 (21 warps)
+using Cfg4 = IsectCfg<256, 13, 9, 3>;   // W=3328 (24 warps)
+using Cfg5 = IsectCfg<192, 15, 9, 3>;   // W=2880, more prefetch slack
 constexpr int N_CFG = 6;
-constexpr int DEFAULT_CFG = 1;
+constexpr int DEFAULT_CFG = 0;
 
 static int g_cfg = DEFAULT_CFG;
 
