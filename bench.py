@@ -224,17 +224,28 @@ def main():
 
     def one_step(text):
         """one pass of the hot path over the whole workload; returns engine metrics"""
+        t_start = time.perf_counter()
         eng.reset()
         for r in range(len(my_ids)):
             eng.add(text[r])
+        t_add = time.perf_counter()
         eng.build()
+        t_build = time.perf_counter()
+        t_xchg = t_build
         if world > 1:
             id_map = sharding.exchange_sets(eng, N, world, rank, dev)
+            torch.cuda.synchronize()
+            t_xchg = time.perf_counter()
             ia, ib = sharding.local_pair_ids(id_map, N, first_pair, n_my_pairs)
             eng.pairs(ia, ib, inter_out=inter, dist_out=dist_out)
         else:
             eng.all_vs_all_range(N, first_pair, n_my_pairs, inter_out=inter, dist_out=dist_out)
-        return eng.metrics()
+        m = eng.metrics()
+        m["wall_add_ms"] = 1e3 * (t_add - t_start)
+        m["wall_build_ms"] = 1e3 * (t_build - t_add)
+        m["wall_exchange_ms"] = 1e3 * (t_xchg - t_build)
+        m["wall_distance_ms"] = 1e3 * (time.perf_counter() - t_xchg)
+        return m
 
     def barrier():
         torch.cuda.synchronize()
@@ -319,7 +330,9 @@ def main():
               "unique_ms": sum(m["unique_ms"] for m in mets) / len(mets),
               "intersect_ms": isect_ms, "epilogue_ms": sum(m["epilogue_ms"] for m in mets) / len(mets),
               "kmers_hashed_per_s_this_rank": kpos / (build_ms * 1e-3) if build_ms > 0 else 0.0,
-              "sort_passes": mets[-1]["sort_passes"]}
+              "sort_passes": mets[-1]["sort_passes"],
+              "wall_ms": {k: sum(m[k] for m in mets) / len(mets) for k in
+                          ("wall_add_ms", "wall_build_ms", "wall_exchange_ms", "wall_distance_ms")}}
 
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:

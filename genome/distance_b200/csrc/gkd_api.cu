@@ -77,7 +77,8 @@ struct gkd_ctx {
     uint32_t built_upto = 0;
 
     std::vector<Slab> slabs;
-    std::vector<void *> set_arenas;
+    std::vector<std::pair<void *, uint64_t>> set_arenas;   // live set arenas (ptr, bytes)
+    std::vector<std::pair<void *, uint64_t>> free_arenas;  // arenas released by gkd_reset, reused best-fit
 
     char *bounce[N_STAGE] = {nullptr, nullptr, nullptr};
     cudaEvent_t bounce_ev[N_STAGE] = {nullptr, nullptr, nullptr};
@@ -302,8 +303,22 @@ int finish_batch(gkd_ctx *c, const std::vector<BatchGenome> &bg, const std::vect
         if (np) arena_keys += set_padded(np);
     }
     void *arena = nullptr;
-    CK(cudaMallocAsync(&arena, arena_keys * 8 + 256, c->stream));
-    c->set_arenas.push_back(arena);
+    {
+        // reuse an arena released by gkd_reset (best fit) so repeated runs do not make the pool remap
+        const uint64_t need = arena_keys * 8 + 256;
+        int best = -1;
+        for (size_t i = 0; i < c->free_arenas.size(); i++)
+            if (c->free_arenas[i].second >= need && (best < 0 || c->free_arenas[i].second < c->free_arenas[best].second))
+                best = (int)i;
+        if (best >= 0) {
+            arena = c->free_arenas[best].first;
+            c->set_arenas.push_back(c->free_arenas[best]);
+            c->free_arenas.erase(c->free_arenas.begin() + best);
+        } else {
+            CK(cudaMallocAsync(&arena, need, c->stream));
+            c->set_arenas.push_back({arena, need});
+        }
+    }
     std::vector<UniqueDst> dst(n);
     uint64_t *cur = (uint64_t *)arena;
     for (uint32_t i = 0; i < n; i++) {
@@ -641,8 +656,16 @@ int gkd_reset(gkd_ctx *c) {
     CHECK_CTX(c);
     CK(cudaSetDevice(c->cfg.device));
     CK(cudaStreamSynchronize(c->stream));
-    for (void *a : c->set_arenas) CK(cudaFreeAsync(a, c->stream));
+    for (auto &a : c->set_arenas) c->free_arenas.push_back(a);
     c->set_arenas.clear();
+    // keep at most a handful of spare arenas; release the smallest ones beyond that
+    while (c->free_arenas.size() > 16) {
+        size_t small = 0;
+        for (size_t i = 1; i < c->free_arenas.size(); i++)
+            if (c->free_arenas[i].second < c->free_arenas[small].second) small = i;
+        CK(cudaFreeAsync(c->free_arenas[small].first, c->stream));
+        c->free_arenas.erase(c->free_arenas.begin() + small);
+    }
     for (auto &s : c->slabs) s.used = 0;
     c->genomes.clear();
     c->built_upto = 0;
@@ -658,7 +681,8 @@ int gkd_destroy(gkd_ctx *c) {
     if (!c) return GKD_EINVAL;
     cudaSetDevice(c->cfg.device);
     cudaStreamSynchronize(c->stream);
-    for (void *a : c->set_arenas) cudaFreeAsync(a, c->stream);
+    for (auto &a : c->set_arenas) cudaFreeAsync(a.first, c->stream);
+    for (auto &a : c->free_arenas) cudaFreeAsync(a.first, c->stream);
     for (auto &s : c->slabs) cudaFreeAsync(s.base, c->stream);
     DevBuf *bufs[] = {&c->keys_a, &c->keys_b, &c->tile_hist, &c->tile_uniq, &c->genome_counts, &c->batch_genomes,
                       &c->uniq_dst, &c->d_sets, &c->counts, &c->pal_counts, &c->d_inter, &c->d_dist, &c->ids_a,
@@ -801,40 +825,58 @@ int gkd_set_device_ptr(const gkd_ctx *c, uint32_t id, const uint64_t **keys, uin
     return GKD_OK;
 }
 
-int gkd_import_set(gkd_ctx *c, const uint64_t *keys, uint64_t n, uint32_t *out_id) {
+int gkd_import_sets(gkd_ctx *c, const uint64_t *keys, const uint64_t *offsets, uint32_t n_sets, uint32_t *first_id) {
     CHECK_CTX(c);
-    if (n && !keys) return fail(c, GKD_EINVAL, "gkd_import_set: null keys");
-    if (n >= 0xFFFF0000ull) return fail(c, GKD_EINVAL, "gkd_import_set: set too large");
+    if (n_sets == 0) {
+        if (first_id) *first_id = (uint32_t)c->genomes.size();
+        return GKD_OK;
+    }
+    if (!offsets) return fail(c, GKD_EINVAL, "gkd_import_sets: null offsets");
+    const uint64_t total = offsets[n_sets];
+    if (total && !keys) return fail(c, GKD_EINVAL, "gkd_import_sets: null keys");
     CK(cudaSetDevice(c->cfg.device));
-    // treat the array as an already-sorted batch of one genome and run the unique/compact pass:
-    // that re-derives the palindrome list and drops any duplicate the caller left in
-    GenomeRec g;
-    g.n_pos = 0;
-    uint32_t id = (uint32_t)c->genomes.size();
-    c->genomes.push_back(g);
-    std::vector<BatchGenome> bg(1);
-    bg[0].codes = nullptr;
-    bg[0].mask = nullptr;
-    bg[0].raw_off = 0;
-    bg[0].n_pos = 0;
-    bg[0].n_slots = (uint32_t)n;
-    bg[0].tile_first = 0;
-    bg[0].n_tiles = (uint32_t)((n + SORT_TILE - 1) / SORT_TILE);
+    // treat the arrays as an already-sorted batch and run the unique/compact pass: that re-derives
+    // the palindrome lists and drops any duplicate the caller left in
+    const uint32_t id0 = (uint32_t)c->genomes.size();
+    std::vector<BatchGenome> bg(n_sets);
+    std::vector<uint32_t> ids(n_sets);
+    uint32_t tiles = 0;
+    for (uint32_t i = 0; i < n_sets; i++) {
+        if (offsets[i + 1] < offsets[i] || offsets[i + 1] - offsets[i] >= 0xFFFF0000ull)
+            return fail(c, GKD_EINVAL, "gkd_import_sets: bad offsets at set %u", i);
+        bg[i].codes = nullptr;
+        bg[i].mask = nullptr;
+        bg[i].raw_off = offsets[i];
+        bg[i].n_pos = 0;
+        bg[i].n_slots = (uint32_t)(offsets[i + 1] - offsets[i]);
+        bg[i].tile_first = tiles;
+        bg[i].n_tiles = (bg[i].n_slots + SORT_TILE - 1) / SORT_TILE;
+        tiles += bg[i].n_tiles;
+        ids[i] = id0 + i;
+    }
+    const bool on_device = total && classify(keys) == MEM_DEVICE;
     SortPlan plan{};
-    int rc = plan_batch(c, bg, plan, std::max<uint64_t>(n, 16), bg[0].n_tiles);
+    int rc = plan_batch(c, bg, plan, on_device ? 16 : std::max<uint64_t>(total, 16), tiles);
+    if (rc) return rc;
+    const uint64_t *sorted = keys;
+    if (!on_device) {
+        if (total) CK(cudaMemcpyAsync(plan.keys_a, keys, total * 8, cudaMemcpyHostToDevice, c->stream));
+        sorted = plan.keys_a;
+        c->m.h2d_bytes += total * 8;
+    }
+    for (uint32_t i = 0; i < n_sets; i++) c->genomes.push_back(GenomeRec());
+    rc = finish_batch(c, bg, ids, plan, sorted);
     if (rc) {
-        c->genomes.pop_back();
+        c->genomes.resize(id0);
         return rc;
     }
-    if (n) CK(cudaMemcpyAsync(plan.keys_a, keys, n * 8, cudaMemcpyDefault, c->stream));
-    std::vector<uint32_t> ids(1, id);
-    rc = finish_batch(c, bg, ids, plan, plan.keys_a);
-    if (rc) {
-        c->genomes.pop_back();
-        return rc;
-    }
-    if (out_id) *out_id = id;
+    if (first_id) *first_id = id0;
     return GKD_OK;
+}
+
+int gkd_import_set(gkd_ctx *c, const uint64_t *keys, uint64_t n, uint32_t *out_id) {
+    uint64_t offsets[2] = {0, n};
+    return gkd_import_sets(c, keys, offsets, 1, out_id);
 }
 
 int gkd_all_vs_all(gkd_ctx *c, uint64_t *inter, double *dist) {

@@ -165,6 +165,26 @@ class Engine:
         del keep
         return out.value
 
+    def import_sets(self, keys, offsets) -> int:
+        """Adopt many sorted key arrays stored back to back (`keys`: numpy uint64 or torch int64 tensor,
+        host or this device; `offsets`: n+1 host integers).  Returns the id of the first new set."""
+        offs = np.ascontiguousarray(offsets, dtype=np.uint64)
+        if isinstance(keys, np.ndarray):
+            a = np.ascontiguousarray(keys, dtype=np.uint64)
+            ptr, keep = a.ctypes.data, a
+        else:
+            import torch
+
+            t = keys.contiguous()
+            if t.is_cuda:
+                torch.cuda.synchronize(self.device)
+            ptr, keep = t.data_ptr(), t
+        out = C.c_uint32()
+        self._ck(self._L.gkd_import_sets(self._h, ptr if int(offs[-1]) else None,
+                                         offs.ctypes.data_as(C.POINTER(C.c_uint64)), offs.size - 1, C.byref(out)))
+        del keep
+        return out.value
+
     # -- distances ---------------------------------------------------------------------------------
     @staticmethod
     def _outs(n: int, inter_out, dist_out, want_inter: bool, want_dist: bool):

@@ -90,20 +90,30 @@ def exchange_sets(eng, n_genomes: int, world: int, rank: int, device) -> Dict[in
     all_sizes = [torch.zeros(per, dtype=torch.int64, device=device) for _ in range(world)]
     dist.all_gather(all_sizes, sizes)
     all_sizes = [t.cpu().tolist() for t in all_sizes]
-    max_n = max(max(s) for s in all_sizes) if all_sizes else 0
-    recv = torch.empty(max(max_n, 1), dtype=torch.int64, device=device)
+    batched = hasattr(eng, "import_sets")
     for owner in range(world):
-        for li, g in enumerate(genome_slice(n_genomes, world, owner)):
-            n = int(all_sizes[owner][li])
-            if owner == rank:
-                t = eng.set_tensor(li)
-                if n:
-                    dist.broadcast(t, src=owner)
-            else:
-                buf = recv[:n]
-                if n:
-                    dist.broadcast(buf, src=owner)
-                id_map[g] = eng.import_set(buf)
+        theirs = genome_slice(n_genomes, world, owner)
+        sizes_o = [int(all_sizes[owner][li]) for li in range(len(theirs))]
+        if owner == rank:
+            for li in range(len(theirs)):
+                if sizes_o[li]:
+                    dist.broadcast(eng.set_tensor(li), src=owner)
+            continue
+        # receive the owner's sets back to back, then adopt them in one batched pass
+        offs = np.zeros(len(theirs) + 1, dtype=np.uint64)
+        offs[1:] = np.cumsum(np.asarray(sizes_o, dtype=np.uint64))
+        recv = torch.empty(max(int(offs[-1]), 1), dtype=torch.int64, device=device)
+        for li in range(len(theirs)):
+            if sizes_o[li]:
+                dist.broadcast(recv[int(offs[li]):int(offs[li + 1])], src=owner)
+        if batched:
+            first = eng.import_sets(recv, offs)
+            for li, g in enumerate(theirs):
+                id_map[g] = first + li
+        else:
+            for li, g in enumerate(theirs):
+                id_map[g] = eng.import_set(recv[int(offs[li]):int(offs[li + 1])])
+        del recv
     return id_map
 
 

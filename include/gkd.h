@@ -125,6 +125,10 @@ int gkd_set_device_ptr(const gkd_ctx *ctx, uint32_t id, const uint64_t **keys, u
 /* adopt a prebuilt sorted key array (host or device pointer; copied) as a new set, e.g. one received
  * from another rank.  The unique/compact pass is re-run on it, which re-derives the palindrome list. */
 int gkd_import_set(gkd_ctx *ctx, const uint64_t *keys, uint64_t n, uint32_t *out_id);
+/* same for n_sets arrays stored back to back: set i is keys[offsets[i] .. offsets[i+1]) (offsets is a
+ * HOST array of n_sets+1 entries; keys may be host or device memory).  One batched pass, one
+ * synchronisation; ids first_id .. first_id+n_sets-1 are assigned in order. */
+int gkd_import_sets(gkd_ctx *ctx, const uint64_t *keys, const uint64_t *offsets, uint32_t n_sets, uint32_t *first_id);
 
 /* ---- distances: kernels 4 + 5 --------------------------------------------------------------- */
 /* All pairs i<j in id order, row-major strict upper triangle of length N*(N-1)/2
