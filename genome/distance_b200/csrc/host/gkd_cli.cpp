@@ -3,6 +3,8 @@
 //
 //   fastaDist  -> FastaDistanceProcessor.java  (options :66-90, validation :93-112, report :134-194)
 //   genomes    -> GenomeProcessor.java         (options :54-79, validation :82-116, report :119-150)
+//   fastaReps  -> FastaDistanceRepsProcessor.java (options :52-76, validation :78-91, report :110-147);
+//                 a caller of the same distance(), SURVEY section 8f "next" row 1
 //
 // Dispatch mirrors App.java:35-111 (args[0] selects the processor).  Reports go to stdout or -o,
 // log lines to stderr (logback.xml:4-13).  Every distance comes from libgkd.so; there is no CPU path.
@@ -187,6 +189,84 @@ int fastaDist(const std::vector<std::string> &args) {
     }
     writer.flush();
     logInfo(std::to_string(t) + " pairs computed in 1 batches.");
+    return 0;
+}
+
+// ---- fastaReps -----------------------------------------------------------------------------------
+const std::vector<OptSpec> REPS_OPTS = {
+    {{"--input", "-i"}, true, "input FASTA file (if not STDIN)"},
+    {{"--kSize", "--kmerSize", "-K"}, true, "kmer size to use; 0 for sequence type default"},
+    {{"--dist", "--maxDist", "-d"}, true, "maximum distance a neighbor can be from a representative"},
+    {{"--type"}, true, "input sequence type"},
+    {{"--output", "-o"}, true, "output file for report (if not STDOUT)"},
+    {{"--device"}, true, "CUDA device ordinal (additive option; default 0)"},
+    {{"--help", "-h"}, false, "display command-line usage"},
+    {{"--verbose", "-v"}, false, "display more frequent log messages"},
+};
+
+int fastaReps(const std::vector<std::string> &args) {
+    Parsed p = parseOptions(REPS_OPTS, args);
+    if (p.values.count("--help")) {
+        printUsage("fastaReps", REPS_OPTS, "");
+        return 0;
+    }
+    // setReporterDefaults (:71-76)
+    std::string inFile = p.values.count("--input") ? p.values["--input"] : "";
+    int kmerSize = p.values.count("--kSize") ? toInt("--kSize", p.values["--kSize"]) : 0;
+    double maxDist = p.values.count("--dist") ? toDouble("--dist", p.values["--dist"]) : 0.97;
+    KmerType seqType = p.values.count("--type") ? parseKmerType(p.values["--type"]) : KmerType::DNA;
+    int device = p.values.count("--device") ? toInt("--device", p.values["--device"]) : 0;
+    // validateReporterParms (:79-91)
+    if (kmerSize == 0) kmerSize = kmerTypeDefaultK(seqType);
+    if (kmerSize < 2) throw ParseFailureException("Kmer size must be at least 2.");
+    if (!inFile.empty() && !readable(inFile)) throw IOException("Input file " + inFile + " is not found or invalid.");
+    std::ofstream ofile;
+    if (p.values.count("--output")) {
+        ofile.open(p.values["--output"]);
+        if (!ofile) throw IOException("Cannot open output file " + p.values["--output"] + ".");
+    }
+    std::ostream &writer = p.values.count("--output") ? (std::ostream &)ofile : std::cout;
+
+    KmerEngine engine(seqType, kmerSize, device);
+    std::vector<SequenceKmers> seqs = engine.addFasta(inFile.empty() ? "-" : inFile);
+    engine.build();  // every createKmers (:122) in one batched pass
+    // runReporter (:110-147): a sequence becomes a representative unless some current representative
+    // is within maxDist.  repMap is keyed by label, so a later representative with the same label
+    // replaces the earlier one (HashMap.put, :145).
+    writer << "seq\tname\n";
+    std::vector<std::pair<std::string, uint32_t>> repMap;  // insertion-ordered label -> set handle
+    std::vector<uint32_t> a, b;
+    std::vector<double> dist;
+    size_t pairCount = 0;
+    for (auto &seq : seqs) {
+        bool repFound = false;
+        if (!repMap.empty()) {
+            a.clear();
+            b.clear();
+            for (auto &r : repMap) {
+                a.push_back(r.second);        // repKmers.distance(seqKmers) (:128)
+                b.push_back(seq.handle());
+            }
+            dist.assign(a.size(), 1.0);
+            engine.check(gkd_pairs(engine.raw(), a.data(), b.data(), a.size(), nullptr, dist.data()));
+            pairCount += a.size();
+            for (double d : dist)
+                if (d <= maxDist) repFound = true;
+        }
+        if (!repFound) {
+            writer << seq.getGenomeId() << '\t' << seq.getGenomeName() << '\n';
+            bool replaced = false;
+            for (auto &r : repMap)
+                if (r.first == seq.getGenomeId()) {
+                    r.second = seq.handle();
+                    replaced = true;
+                }
+            if (!replaced) repMap.emplace_back(seq.getGenomeId(), seq.handle());
+        }
+    }
+    writer.flush();
+    logInfo(std::to_string(repMap.size()) + " representatives found for " + std::to_string(seqs.size()) + " sequences.");
+    (void)pairCount;
     return 0;
 }
 
@@ -415,7 +495,7 @@ int genomes(const std::vector<std::string> &args) {
 
 int main(int argc, char **argv) {
     if (argc < 2) {
-        fprintf(stderr, "usage: gkd <fastaDist|genomes> [options]\n");
+        fprintf(stderr, "usage: gkd <fastaDist|genomes|fastaReps> [options]\n");
         return 2;
     }
     std::string command = argv[1];
@@ -423,12 +503,14 @@ int main(int argc, char **argv) {
     try {
         if (command == "fastaDist") return fastaDist(rest);
         if (command == "genomes") return genomes(rest);
+        if (command == "fastaReps") return fastaReps(rest);
         // App.java:104 -- IllegalArgumentException("Invalid command " + command)
-        fprintf(stderr, "Invalid command %s. (gkd implements the k-mer distance hot path: fastaDist, genomes)\n", command.c_str());
+        fprintf(stderr, "Invalid command %s. (gkd implements the k-mer distance hot path: fastaDist, genomes, fastaReps)\n", command.c_str());
         return 2;
     } catch (const ParseFailureException &e) {
         fprintf(stderr, "%s\n", e.what());  // BaseProcessor prints the message and the usage
-        printUsage(command, command == "genomes" ? GENOME_OPTS : FASTA_OPTS, command == "genomes" ? "gtoDir gtoDir1 gtoDir2 ..." : "");
+        printUsage(command, command == "genomes" ? GENOME_OPTS : (command == "fastaReps" ? REPS_OPTS : FASTA_OPTS),
+                   command == "genomes" ? "gtoDir gtoDir1 gtoDir2 ..." : "");
         return 1;
     } catch (const IOException &e) {
         fprintf(stderr, "%s\n", e.what());

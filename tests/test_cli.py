@@ -115,3 +115,38 @@ def test_genomes_report_matches_oracle_text(orc, tmp_path):
     assert rc == 0, err
     assert out.rstrip("\n").split("\n") == want  # deterministic order in this command
     assert "6 comparisons output." in err
+
+
+def test_fastareps_validation():
+    rc, out, err = run(["fastaReps", "-K", "1"])
+    assert rc == 1 and err.startswith("Kmer size must be at least 2.")
+    rc, out, err = run(["fastaReps", "-i", "/definitely/missing.fa"])
+    assert rc == 1 and "is not found or invalid." in err
+
+
+@pytest.mark.gpu
+def test_fastareps_matches_reference_greedy(orc, tmp_path):
+    """FastaDistanceRepsProcessor.java:117-147: a record is a representative unless a current
+    representative is within --dist; output is `seq\\tname` in input order."""
+    rng = random.Random(21)
+    bases = [_rand(rng, 12000) for _ in range(3)]
+    recs = []
+    for i in range(14):
+        b = bases[i % 3]
+        recs.append(("r%02d" % i, "fam%d" % (i % 3), _mut(rng, b, 0.004 * (i // 3))))
+    fa = tmp_path / "reps.fa"
+    with open(fa, "w") as f:
+        for label, comment, seq in recs:
+            f.write(">%s %s\n%s\n" % (label, comment, seq))
+    sets = [orc.StrSet(s, 21) for _, _, s in recs]
+    for max_dist in (0.97, 0.3, 0.15, 0.05):
+        reps, want = [], ["seq\tname"]
+        for i, (label, comment, _) in enumerate(recs):
+            if not any(sets[r].distance(sets[i]) <= max_dist for r in reps):
+                reps.append(i)
+                want.append(label + "\t" + comment)
+        rc, out, err = run(["fastaReps", "-i", str(fa), "--dist", str(max_dist)])
+        assert rc == 0, err
+        assert out.rstrip("\n").split("\n") == want, max_dist
+        assert "%d representatives found for %d sequences." % (len(reps), len(recs)) in err
+    assert len(want) > 4  # the tightest threshold splits the families

@@ -275,3 +275,64 @@ def test_synth_device_matches_host():
         gkd.synth(d, 3, 4, 2, 0.07, protein=protein)
         gkd.synth(h, 3, 4, 2, 0.07, protein=protein)
         assert np.array_equal(d.cpu().numpy(), h)
+
+
+def test_config3_shape_protein_query_vs_reference(orc):
+    """BASELINE configs[2] shape at reduced size: per-genome protein 8-mer sets (one piece per protein,
+    k-mers never span proteins), queries x references."""
+    rng = random.Random(303)
+
+    def proteome(family, member, rate, n_prot=300):
+        prots = []
+        for p in range(n_prot):
+            n = max(50, min(1500, int(rng.lognormvariate(5.5, 0.5))))
+            a = np.empty(n, dtype=np.uint8)
+            gkd.synth(a, 1000 + p, family, member, rate, protein=True)
+            prots.append(a.tobytes())
+        return prots
+
+    rng_state = rng.getstate()
+    refs, queries = [], []
+    for f in range(2):
+        rng.setstate(rng_state)  # same protein lengths in every member of a family
+        refs.append(proteome(f, 0, 0.0))
+    for q in range(5):
+        rng.setstate(rng_state)
+        queries.append(proteome(q % 2, 1 + q, 0.05 + 0.05 * q))
+    with gkd.Engine(k=8, alphabet=gkd.PROT) as e:
+        rid = [e.add(p) for p in refs]
+        qid = [e.add(p) for p in queries]
+        e.build()
+        gi, gd = e.query_vs_ref(qid, rid)
+    oi, od = np.zeros_like(gi), np.zeros_like(gd)
+    rs = [orc.IntSet(p, 8, orc.PROT) for p in refs]
+    for a, q in enumerate(queries):
+        qs = orc.IntSet(q, 8, orc.PROT)
+        for b in range(len(refs)):
+            oi[a, b], od[a, b] = qs.similarity(rs[b]), qs.distance(rs[b])
+    assert np.array_equal(gi, oi) and np.array_equal(gd, od)
+    assert (gd < 1.0).any() and (gd == 1.0).any()
+    s0, s1 = orc.StrSet(queries[0], 8, orc.PROT), orc.StrSet(refs[0], 8, orc.PROT)
+    assert gi[0, 0] == s0.similarity(s1) and gd[0, 0] == s0.distance(s1)
+
+
+def test_config5_shape_skewed_sizes(orc):
+    """BASELINE configs[4] shape: plasmid-scale to 12 Mbp genomes in one all-vs-all (uneven set sizes
+    exercise the (pair, segment) work split)."""
+    import torch
+
+    lens = [100_000, 12_000_000, 350_000, 1_300_000, 5_000_000, 100_000, 2_400_000]
+    seqs = []
+    for g, n in enumerate(lens):
+        t = torch.empty(n, dtype=torch.uint8, device="cuda")
+        gkd.synth(t, 55, g % 2, g // 2, 0.01 * (g // 2))
+        seqs.append(t)
+    with gkd.Engine(k=21) as e:
+        for t in seqs:
+            e.add(t)
+        e.build()
+        gi, gd = e.all_vs_all()
+    osets = [orc.IntSet(t.cpu().numpy().tobytes(), 21) for t in seqs]
+    want_i = [osets[i].similarity(osets[j]) for i in range(len(lens)) for j in range(i + 1, len(lens))]
+    want_d = [osets[i].distance(osets[j]) for i in range(len(lens)) for j in range(i + 1, len(lens))]
+    assert gi.tolist() == want_i and gd.tolist() == want_d
