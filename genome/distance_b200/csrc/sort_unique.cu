@@ -127,15 +127,19 @@ __global__ void __launch_bounds__(SORT_THREADS)
         uint32_t idx = warp * (32 * SORT_ITEMS) + i * 32 + lane;
         key[i] = idx < count ? src[idx] : KEY_SENTINEL;  // padding ranks after every real key
     }
+    // Rank = (keys of the same digit seen by this warp in earlier items) + (same-digit lanes below me).
+    // The first part comes from ONE shared-memory atomic per digit group per item, issued by the
+    // group's lowest lane; atomics to one address retire in issue order, so no __syncwarp is needed
+    // and the 16 match/atomic/shuffle chains overlap instead of serialising on shared memory.
 #pragma unroll
     for (int i = 0; i < SORT_ITEMS; i++) {
-        uint32_t d = (uint32_t)(key[i] >> shift) & dmask;
-        uint32_t peers = __match_any_sync(0xffffffffu, d);
-        uint32_t prev = s_cnt[warp][d];
-        __syncwarp();
+        const uint32_t d = (uint32_t)(key[i] >> shift) & dmask;
+        const uint32_t peers = __match_any_sync(0xffffffffu, d);
+        const int leader = __ffs(peers) - 1;
+        uint32_t prev = 0;
+        if (lane == leader) prev = atomicAdd(&s_cnt[warp][d], (uint32_t)__popc(peers));
+        prev = __shfl_sync(0xffffffffu, prev, leader);
         rank[i] = prev + __popc(peers & lt_mask);
-        if (lane == __ffs(peers) - 1) s_cnt[warp][d] = prev + __popc(peers);
-        __syncwarp();
     }
     __syncthreads();
     {   // thread d: exclusive scan over warps for digit d, then over digits
