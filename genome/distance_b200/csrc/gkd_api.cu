@@ -275,6 +275,9 @@ int add_genome(gkd_ctx *c, const std::vector<Part> &parts, const std::string &la
         c->m.launches++;
         q0 = q1;
     } while (q0 < n_pos);
+    // contract (gkd.h): inputs are consumed before the call returns.  Pageable text was copied into the
+    // bounce buffers synchronously; pinned/device text is read by stream-ordered copies, so wait for them.
+    if (kind != MEM_PAGEABLE) CK(cudaStreamSynchronize(c->stream));
     c->m.residues_packed += n_pos;
     if (out_id) *out_id = (uint32_t)c->genomes.size();
     c->genomes.push_back(std::move(g));
