@@ -52,7 +52,7 @@ def c1():
         h = dev.cpu().numpy()
         oa, ob = orc.IntSet(h[0].tobytes(), 21), orc.IntSet(h[1].tobytes(), 21)
         ok = int(inter[0]) == oa.similarity(ob) and dist[0] == oa.distance(ob)
-        finish("c1: 2 x 5 Mbp DNA K=21", e, 1, t1 - t0, t2 - t1, {"distance": gkd.format_double(float(dist[0])), "oracle_match": ok})
+        finish("c1: 2 x 5 Mbp DNA K=21", e, 1, t1 - t0, t2 - t1, {"distance": gkd.format_double(float(dist[0])), "oracle_match": bool(ok)})
 
 
 def c3(nq, nr, n_prot):
@@ -69,6 +69,9 @@ def c3(nq, nr, n_prot):
         return buf
 
     with gkd.Engine(k=8, alphabet=gkd.PROT, workspace_bytes=24 << 30) as e:
+      for rep in range(2):  # second pass reuses the device pools (steady state)
+        e.reset()
+        torch.cuda.synchronize()
         t0 = time.perf_counter()
         rid = [e.add(proteome(r % 25, 0 if r < 25 else r, 0.0 if r < 25 else 0.05 + 0.01 * (r % 25))) for r in range(nr)]
         qid = [e.add(proteome(q % 25, 1000 + q, 0.05 + 0.25 * ((q * 7919) % 100) / 100.0)) for q in range(nq)]
@@ -76,7 +79,8 @@ def c3(nq, nr, n_prot):
         t1 = time.perf_counter()
         inter, dist = e.query_vs_ref(qid, rid)
         t2 = time.perf_counter()
-        # oracle spot check of one related and one unrelated pair
+      if True:
+        # spot check of two pairs against a host intersection of the exported sets
         ok = True
         for (a, b) in ((0, 0), (1, 0)):
             qa, rb = e.export_set(qid[a]), e.export_set(rid[b])
@@ -90,6 +94,9 @@ def c5(n):
     lens = np.exp(rng.uniform(math.log(1e5), math.log(12e6), n)).astype(np.int64)
     buf = torch.empty(int(lens.max()), dtype=torch.uint8, device="cuda")
     with gkd.Engine(k=21) as e:
+      for rep in range(2):  # second pass reuses the device pools (steady state)
+        e.reset()
+        torch.cuda.synchronize()
         t0 = time.perf_counter()
         for g in range(n):
             v = buf[: int(lens[g])]
@@ -99,6 +106,7 @@ def c5(n):
         t1 = time.perf_counter()
         inter, dist = e.all_vs_all()
         t2 = time.perf_counter()
+      if True:
         a, b = e.export_set(0), e.export_set(20)  # same family, different lengths
         t = 19  # pair (0, 20) in row-major order
         ok = int(inter[t]) == 2 * int(np.intersect1d(a, b, assume_unique=True).size)
