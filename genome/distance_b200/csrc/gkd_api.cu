@@ -503,6 +503,13 @@ int run_pairs(gkd_ctx *c, const HostPairs &hp, uint64_t *inter, double *dist) {
     c->m.intersect_bytes = (uint64_t)sum_bytes;
     if (hp.count == 0) return GKD_OK;
 
+    // palindrome side lists are tiny; the largest one decides which kernel intersects them
+    uint64_t max_pal = 0;
+    if (need_pal)
+        for (auto &g : c->genomes) max_pal = std::max<uint64_t>(max_pal, g.desc.n_pal);
+    const bool small_main = c->cfg.segment_keys == 0 && max_n <= intersect_small_max_keys();
+    const bool small_pal = max_pal <= intersect_small_max_keys();
+
     // merge-path segmenting: whole pairs when there are enough of them to fill the machine
     const uint64_t max_l = std::max<uint64_t>(2 * max_n, 1);
     const uint64_t target_items = (uint64_t)c->n_sms * 3 * 8;
@@ -559,14 +566,22 @@ int run_pairs(gkd_ctx *c, const HostPairs &hp, uint64_t *inter, double *dist) {
         if (dist && (rc = ensure(c, c->d_dist, cnt * 8))) return rc;
 
         CK(cudaEventRecord(c->ev[4], c->stream));
-        CK(launch_intersect((const SetDesc *)c->d_sets.p, src, 0, (uint32_t)seg, max_segs, (uint32_t *)c->counts.p,
-                            (unsigned long long *)c->work_counter.p, c->n_sms, c->stream));
+        if (small_main)
+            CK(launch_intersect_small((const SetDesc *)c->d_sets.p, src, 0, (uint32_t *)c->counts.p, c->n_sms, c->stream));
+        else
+            CK(launch_intersect((const SetDesc *)c->d_sets.p, src, 0, (uint32_t)seg, max_segs, (uint32_t *)c->counts.p,
+                                (unsigned long long *)c->work_counter.p, c->n_sms, c->stream));
         CK(cudaEventRecord(c->ev[5], c->stream));
         c->m.launches++;
         c->m.intersect_launches++;
         if (need_pal) {
-            CK(launch_intersect((const SetDesc *)c->d_sets.p, src, 1, (uint32_t)seg, max_segs, (uint32_t *)c->pal_counts.p,
-                                (unsigned long long *)c->work_counter.p, c->n_sms, c->stream));
+            if (small_pal)
+                CK(launch_intersect_small((const SetDesc *)c->d_sets.p, src, 1, (uint32_t *)c->pal_counts.p, c->n_sms,
+                                          c->stream));
+            else
+                CK(launch_intersect((const SetDesc *)c->d_sets.p, src, 1, (uint32_t)seg, max_segs,
+                                    (uint32_t *)c->pal_counts.p, (unsigned long long *)c->work_counter.p, c->n_sms,
+                                    c->stream));
             c->m.launches++;
         }
         CK(cudaEventRecord(c->ev[6], c->stream));

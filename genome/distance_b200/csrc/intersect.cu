@@ -420,6 +420,61 @@ cudaError_t launch_intersect(const SetDesc *sets, PairSource src, int use_pal, u
     return cudaErrorInvalidValue;
 }
 
+// ---- kernel 4, small-set variant ---------------------------------------------------------------------
+// When every set is small (gene/protein-sized FASTA records: the whole pair is a few KiB and stays in
+// L1/L2) the streaming kernel's per-item set-up dominates.  Here one warp owns a pair: each lane takes
+// keys of the smaller set and binary-searches them in the larger one (sentinel-padded, so no bound
+// check on the final probe); counts are combined with shuffles and written without atomics.
+constexpr uint32_t SMALL_SET_MAX_KEYS = 16384;
+
+__global__ void __launch_bounds__(256)
+    k_intersect_small(const SetDesc *__restrict__ sets, PairSource src, int use_pal, uint32_t *__restrict__ counts) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint64_t warps = (uint64_t)gridDim.x * (blockDim.x >> 5);
+    for (uint64_t t = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); t < src.count; t += warps) {
+        uint32_t ida, idb;
+        decode_pair(src, t, ida, idb);
+        const SetDesc SA = sets[ida], SB = sets[idb];
+        const uint64_t *ka = use_pal ? SA.pal_keys : SA.keys, *kb = use_pal ? SB.pal_keys : SB.keys;
+        uint32_t na = use_pal ? SA.n_pal : SA.n, nb = use_pal ? SB.n_pal : SB.n;
+        if (na > nb) {
+            const uint64_t *tk = ka;
+            ka = kb;
+            kb = tk;
+            uint32_t tn = na;
+            na = nb;
+            nb = tn;
+        }
+        uint32_t cnt = 0;
+        if (na != 0) {  // then nb != 0 and kb is padded with sentinels past nb
+            for (uint32_t i = lane; i < na; i += 32) {
+                const uint64_t key = __ldg(ka + i);
+                uint32_t lo = 0, hi = nb;
+                while (lo < hi) {
+                    const uint32_t mid = (lo + hi) >> 1;
+                    if (__ldg(kb + mid) < key) lo = mid + 1;
+                    else hi = mid;
+                }
+                cnt += (__ldg(kb + lo) == key) ? 1u : 0u;
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+        if (lane == 0) counts[t] = cnt;
+    }
+}
+
+cudaError_t launch_intersect_small(const SetDesc *sets, PairSource src, int use_pal, uint32_t *counts, int n_sms,
+                                   cudaStream_t s) {
+    if (src.count == 0) return cudaSuccess;
+    uint64_t grid = (src.count + 7) / 8;
+    if (grid > (uint64_t)n_sms * 8) grid = (uint64_t)n_sms * 8;
+    k_intersect_small<<<(unsigned)grid, 256, 0, s>>>(sets, src, use_pal, counts);
+    return cudaGetLastError();
+}
+
+uint32_t intersect_small_max_keys() { return SMALL_SET_MAX_KEYS; }
+
 // ---- kernel 5: distance epilogue ----------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
     k_epilogue(const SetDesc *__restrict__ sets, PairSource src, const uint32_t *__restrict__ counts,

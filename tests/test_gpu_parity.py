@@ -336,3 +336,26 @@ def test_config5_shape_skewed_sizes(orc):
     want_i = [osets[i].similarity(osets[j]) for i in range(len(lens)) for j in range(i + 1, len(lens))]
     want_d = [osets[i].distance(osets[j]) for i in range(len(lens)) for j in range(i + 1, len(lens))]
     assert gi.tolist() == want_i and gd.tolist() == want_d
+
+
+@pytest.mark.parametrize("k,alpha", [(21, "DNA"), (12, "DNA"), (8, "PROT")])
+def test_many_small_sequences_all_vs_all(orc, k, alpha):
+    """fastaDist's own use case: hundreds of gene/protein-sized records (warp-per-pair kernel)."""
+    rng = random.Random(900 + k)
+    letters = "ACDEFGHIKLMNPQRSTVWY" if alpha == "PROT" else "acgt"
+    al = gkd.PROT if alpha == "PROT" else gkd.DNA
+    oal = orc.PROT if alpha == "PROT" else orc.DNA
+    bases = [_rand_dna(rng, rng.randint(300, 3000), letters) for _ in range(12)]
+    seqs = []
+    for i in range(150):
+        s = _mutate(rng, bases[i % 12], 0.01 * (i // 12), letters)
+        seqs.append(s[: rng.randint(len(s) // 2, len(s))] if i % 7 == 0 else s)
+    seqs += ["", letters[:3], _rand_dna(rng, k, letters)]
+    with gkd.Engine(k=k, alphabet=al) as e:
+        for s in seqs:
+            e.add(s)
+        e.build()
+        gi, gd = e.all_vs_all()
+    oi, od = orc.fasta_dist(seqs, k, alphabet=oal, batch=20, threads=0, mode=1)
+    assert np.array_equal(gi, oi) and np.array_equal(gd, od)
+    assert (gd < 0.5).any() and (gd == 1.0).any()
