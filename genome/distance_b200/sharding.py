@@ -90,7 +90,33 @@ def exchange_sets(eng, n_genomes: int, world: int, rank: int, device) -> Dict[in
     all_sizes = [torch.zeros(per, dtype=torch.int64, device=device) for _ in range(world)]
     dist.all_gather(all_sizes, sizes)
     all_sizes = [t.cpu().tolist() for t in all_sizes]
-    batched = hasattr(eng, "import_sets")
+    if hasattr(eng, "import_sets") and hasattr(dist, "all_gather_into_tensor"):
+        # ONE collective: every rank packs its sets back to back into a send buffer padded to the
+        # largest per-rank total, all_gather_into_tensor moves them at full NVLink bandwidth, and each
+        # peer's segment is adopted with one batched import.
+        totals = [sum(int(x) for x in all_sizes[o][: len(genome_slice(n_genomes, world, o))]) for o in range(world)]
+        cap = max(max(totals), 1)
+        send = torch.empty(cap, dtype=torch.int64, device=device)
+        off = 0
+        for i in range(len(mine)):
+            t = eng.set_tensor(i)
+            send[off:off + t.numel()].copy_(t)
+            off += t.numel()
+        gathered = torch.empty(world * cap, dtype=torch.int64, device=device)
+        dist.all_gather_into_tensor(gathered, send)
+        del send
+        for owner in range(world):
+            if owner == rank:
+                continue
+            theirs = genome_slice(n_genomes, world, owner)
+            offs = np.zeros(len(theirs) + 1, dtype=np.uint64)
+            offs[1:] = np.cumsum(np.asarray([int(all_sizes[owner][li]) for li in range(len(theirs))], dtype=np.uint64))
+            first = eng.import_sets(gathered[owner * cap: owner * cap + int(offs[-1])], offs)
+            for li, g in enumerate(theirs):
+                id_map[g] = first + li
+        del gathered
+        return id_map
+    # generic path (any engine with import_set; used by the CPU/gloo tests): one broadcast per set
     for owner in range(world):
         theirs = genome_slice(n_genomes, world, owner)
         sizes_o = [int(all_sizes[owner][li]) for li in range(len(theirs))]
@@ -99,20 +125,12 @@ def exchange_sets(eng, n_genomes: int, world: int, rank: int, device) -> Dict[in
                 if sizes_o[li]:
                     dist.broadcast(eng.set_tensor(li), src=owner)
             continue
-        # receive the owner's sets back to back, then adopt them in one batched pass
-        offs = np.zeros(len(theirs) + 1, dtype=np.uint64)
-        offs[1:] = np.cumsum(np.asarray(sizes_o, dtype=np.uint64))
-        recv = torch.empty(max(int(offs[-1]), 1), dtype=torch.int64, device=device)
-        for li in range(len(theirs)):
+        recv = torch.empty(max(max(sizes_o) if sizes_o else 0, 1), dtype=torch.int64, device=device)
+        for li, g in enumerate(theirs):
+            buf = recv[: sizes_o[li]]
             if sizes_o[li]:
-                dist.broadcast(recv[int(offs[li]):int(offs[li + 1])], src=owner)
-        if batched:
-            first = eng.import_sets(recv, offs)
-            for li, g in enumerate(theirs):
-                id_map[g] = first + li
-        else:
-            for li, g in enumerate(theirs):
-                id_map[g] = eng.import_set(recv[int(offs[li]):int(offs[li + 1])])
+                dist.broadcast(buf, src=owner)
+            id_map[g] = eng.import_set(buf)
         del recv
     return id_map
 
