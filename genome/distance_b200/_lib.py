@@ -35,6 +35,7 @@ SYMBOLS = {
     "gkd_create": (_i32, [C.POINTER(_vp), C.POINTER(GkdConfig)]),
     "gkd_destroy": (_i32, [_vp]),
     "gkd_reset": (_i32, [_vp]),
+    "gkd_truncate": (_i32, [_vp, _u32]),
     "gkd_last_error": (C.c_char_p, [_vp]),
     "gkd_add_sequences": (_i32, [_vp, C.POINTER(_vp), _pu64, _u32, _pu32]),
     "gkd_add_fasta_file": (_i32, [_vp, C.c_char_p, _i32, _pu32, _pu32]),

@@ -78,6 +78,7 @@ struct gkd_ctx {
 
     std::vector<Slab> slabs;
     std::vector<std::pair<void *, uint64_t>> set_arenas;   // live set arenas (ptr, bytes)
+    std::vector<uint32_t> arena_first_id;                   // first set id stored in each live arena
     std::vector<std::pair<void *, uint64_t>> free_arenas;  // arenas released by gkd_reset, reused best-fit
 
     char *bounce[N_STAGE] = {nullptr, nullptr, nullptr};
@@ -321,6 +322,7 @@ int finish_batch(gkd_ctx *c, const std::vector<BatchGenome> &bg, const std::vect
             CK(cudaMallocAsync(&arena, need, c->stream));
             c->set_arenas.push_back({arena, need});
         }
+        c->arena_first_id.push_back(ids.empty() ? 0u : ids.front());
     }
     std::vector<UniqueDst> dst(n);
     uint64_t *cur = (uint64_t *)arena;
@@ -676,6 +678,7 @@ int gkd_reset(gkd_ctx *c) {
     CK(cudaStreamSynchronize(c->stream));
     for (auto &a : c->set_arenas) c->free_arenas.push_back(a);
     c->set_arenas.clear();
+    c->arena_first_id.clear();
     // keep at most a handful of spare arenas; release the smallest ones beyond that
     while (c->free_arenas.size() > 16) {
         size_t small = 0;
@@ -692,6 +695,23 @@ int gkd_reset(gkd_ctx *c) {
     c->m = gkd_metrics{};
     c->m.launches = launches;
     c->m.intersect_launches = il;
+    return GKD_OK;
+}
+
+int gkd_truncate(gkd_ctx *c, uint32_t n_keep) {
+    CHECK_CTX(c);
+    if (n_keep >= c->genomes.size()) return GKD_OK;
+    CK(cudaSetDevice(c->cfg.device));
+    CK(cudaStreamSynchronize(c->stream));
+    // arenas are created in id order, one per build/import batch: recycle those that hold only dropped sets
+    while (!c->set_arenas.empty() && c->arena_first_id.back() >= n_keep) {
+        c->free_arenas.push_back(c->set_arenas.back());
+        c->set_arenas.pop_back();
+        c->arena_first_id.pop_back();
+    }
+    c->genomes.resize(n_keep);
+    if (c->built_upto > n_keep) c->built_upto = n_keep;
+    c->sets_dirty = true;
     return GKD_OK;
 }
 

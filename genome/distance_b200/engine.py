@@ -236,6 +236,10 @@ class Engine:
         """cudaStream_t of this context (wrap with torch.cuda.ExternalStream to time on it)"""
         return self._L.gkd_stream(self._h) or 0
 
+    def truncate(self, n_keep: int):
+        """drop the sets with id >= n_keep (a streamed panel) and recycle their arena"""
+        self._ck(self._L.gkd_truncate(self._h, n_keep))
+
     def metrics(self) -> dict:
         m = GkdMetrics()
         self._ck(self._L.gkd_get_metrics(self._h, C.byref(m)))

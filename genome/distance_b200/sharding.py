@@ -142,3 +142,98 @@ def local_pair_ids(id_map: Dict[int, int], n_genomes: int, first: int, count: in
     for g, i in id_map.items():
         lut[g] = i
     return lut[a], lut[b]
+
+
+# ------------------------------------------------------------------------------------------------
+# Streamed column panels: all-vs-all when the sets do not fit one GPU (BASELINE config 4)
+# ------------------------------------------------------------------------------------------------
+def ring_partners(world: int, rank: int):
+    """Steps s = 1..world//2 of the block ring.  Rank x owns block (x, (x+s) % world); for even
+    worlds the half-way step would pair the same two ranks twice, so only the lower rank computes.
+    Returns [(src, recv_needed, dst, send_needed)]: receive src's panel / send own panel to dst."""
+    out = []
+    for s in range(1, world // 2 + 1):
+        src, dst = (rank + s) % world, (rank - s) % world
+        half = world % 2 == 0 and s == world // 2
+        out.append((src, (not half) or rank < src, dst, (not half) or dst < rank))
+    return out
+
+
+def streamed_all_vs_all(eng, n_genomes: int, world: int, rank: int, device, panel_genomes: int = 256):
+    """All-vs-all without ever holding more than (own slice + one sub-panel) of sets per rank.
+
+    Every rank keeps its genome slice resident (built, ids 0..m-1), computes its diagonal block,
+    then walks the ring: the owner of a column panel sends it in sub-panels of `panel_genomes` sets
+    (NCCL send/recv over NVLink), the receiver adopts a sub-panel (`import_sets`), intersects
+    its rows against it (`query_vs_ref`), and drops it (`truncate`).  Every unordered pair of
+    genomes is computed exactly once somewhere; there is no reduction.
+
+    Returns this rank's results as (gi, gj, inter, dist) arrays with global ids gi < gj.
+    """
+    import torch
+    import torch.distributed as dist
+
+    mine = genome_slice(n_genomes, world, rank)
+    m = len(mine)
+    per = (n_genomes + world - 1) // world
+    sizes = torch.zeros(per, dtype=torch.int64, device=device)
+    for i in range(m):
+        sizes[i] = eng.set_tensor(i).numel()
+    all_sizes = [torch.zeros(per, dtype=torch.int64, device=device) for _ in range(world)]
+    dist.all_gather(all_sizes, sizes)
+    all_sizes = [t.cpu().numpy() for t in all_sizes]
+
+    out_i, out_j, out_inter, out_dist = [], [], [], []
+
+    def emit(rows, cols, inter, d):
+        rows, cols = np.asarray(rows, dtype=np.int64), np.asarray(cols, dtype=np.int64)
+        out_i.append(np.minimum(rows, cols))
+        out_j.append(np.maximum(rows, cols))
+        out_inter.append(np.asarray(inter).reshape(-1))
+        out_dist.append(np.asarray(d).reshape(-1))
+
+    # diagonal block: my genomes against each other
+    if m >= 2:
+        cnt = m * (m - 1) // 2
+        inter, d = eng.all_vs_all_range(m, 0, cnt)
+        a, b = pair_lists(m, 0, cnt)
+        base = mine[0]
+        emit(a.astype(np.int64) + base, b.astype(np.int64) + base, inter, d)
+
+    my_rows = np.arange(m, dtype=np.uint32)
+    for src, recv_needed, dst, send_needed in ring_partners(world, rank):
+        theirs = genome_slice(n_genomes, world, src)
+        n_recv = (len(theirs) + panel_genomes - 1) // panel_genomes if recv_needed else 0
+        n_send = (m + panel_genomes - 1) // panel_genomes if send_needed else 0
+        for k in range(max(n_recv, n_send)):
+            reqs, send, recv, offs, chunk = [], None, None, None, None
+            if k < n_send:
+                lo, hi = k * panel_genomes, min(m, (k + 1) * panel_genomes)
+                parts = [eng.set_tensor(i) for i in range(lo, hi)]
+                send = torch.cat(parts) if parts else torch.empty(0, dtype=torch.int64, device=device)
+                if send.numel() == 0:
+                    send = torch.zeros(1, dtype=torch.int64, device=device)
+                reqs.append(dist.isend(send, dst))
+            if k < n_recv:
+                chunk = theirs[k * panel_genomes: (k + 1) * panel_genomes]
+                li0 = k * panel_genomes
+                sz = all_sizes[src][li0: li0 + len(chunk)].astype(np.uint64)
+                offs = np.zeros(len(chunk) + 1, dtype=np.uint64)
+                offs[1:] = np.cumsum(sz)
+                recv = torch.empty(max(int(offs[-1]), 1), dtype=torch.int64, device=device)
+                reqs.append(dist.irecv(recv, src))
+            for r in reqs:
+                r.wait()
+            if recv is not None and m > 0:
+                first = eng.import_sets(recv[: int(offs[-1])], offs)
+                cols = np.arange(first, first + len(chunk), dtype=np.uint32)
+                inter, d = eng.query_vs_ref(my_rows, cols)
+                rows_g = np.repeat(np.asarray(mine, dtype=np.int64), len(chunk))
+                cols_g = np.tile(np.asarray(chunk, dtype=np.int64), m)
+                emit(rows_g, cols_g, inter, d)
+                eng.truncate(m)
+            del send, recv
+    if not out_i:
+        z = np.zeros(0, dtype=np.int64)
+        return z, z, np.zeros(0, dtype=np.uint64), np.zeros(0, dtype=np.float64)
+    return np.concatenate(out_i), np.concatenate(out_j), np.concatenate(out_inter), np.concatenate(out_dist)

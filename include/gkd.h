@@ -93,6 +93,9 @@ int gkd_create(gkd_ctx **out, const gkd_config *cfg);
 int gkd_destroy(gkd_ctx *ctx);
 /* drop every genome and set but keep device pools warm (used between bench steps) */
 int gkd_reset(gkd_ctx *ctx);
+/* drop the sets with id >= n_keep (e.g. a streamed column panel that has been intersected) and
+ * recycle their arena; ids below n_keep stay valid */
+int gkd_truncate(gkd_ctx *ctx, uint32_t n_keep);
 /* message of the last failure on ctx (ctx may be NULL for a failed gkd_create) */
 const char *gkd_last_error(const gkd_ctx *ctx);
 int gkd_abi_version(void);

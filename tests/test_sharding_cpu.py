@@ -115,3 +115,88 @@ def test_exchange_and_pair_slices_over_gloo(orc, world):
     sets = [orc.IntSet(x, k) for x in seqs]
     want = [sets[i].intersect(sets[j])[0] for i in range(n) for j in range(i + 1, n)]
     assert got == want
+
+
+def test_ring_partners_cover_every_rank_pair_once():
+    for world in (1, 2, 3, 4, 5, 8):
+        owned = {}
+        for r in range(world):
+            for src, recv_needed, dst, send_needed in sharding.ring_partners(world, r):
+                if recv_needed:
+                    key = frozenset((r, src))
+                    assert key not in owned, (world, key)
+                    owned[key] = r
+                # what I send must be wanted by the receiver, and vice versa
+                back = [p for p in sharding.ring_partners(world, dst) if p[0] == r]
+                assert len(back) == 1 and back[0][1] == send_needed
+        assert len(owned) == world * (world - 1) // 2
+
+
+class _CpuPanelEngine(_CpuEngine):
+    """adds the batched calls streamed_all_vs_all needs (numpy stand-ins for kernels 4-5)"""
+
+    def _pair(self, i, j):
+        x, y = self.sets[i].numpy(), self.sets[j].numpy()
+        inter = 2 * np.intersect1d(x, y, assume_unique=True).size  # odd K: both-strand count
+        return inter, self.orc.distance(inter, 2 * x.size, 2 * y.size)
+
+    def import_sets(self, t, offs):
+        first = len(self.sets)
+        for a, b in zip(offs[:-1], offs[1:]):
+            self.sets.append(t[int(a):int(b)].clone())
+        return first
+
+    def truncate(self, n):
+        del self.sets[n:]
+
+    def all_vs_all_range(self, n, first, count):
+        a, b = sharding.pair_lists(n, first, count)
+        r = [self._pair(int(i), int(j)) for i, j in zip(a, b)]
+        return np.array([x[0] for x in r], dtype=np.uint64), np.array([x[1] for x in r], dtype=np.float64)
+
+    def query_vs_ref(self, q, r):
+        res = [[self._pair(int(i), int(j)) for j in r] for i in q]
+        return (np.array([[x[0] for x in row] for row in res], dtype=np.uint64).reshape(len(q), len(r)),
+                np.array([[x[1] for x in row] for row in res], dtype=np.float64).reshape(len(q), len(r)))
+
+
+def _stream_worker(rank, world, port, n, length, k, panel, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from oracle import oracle as orc
+
+    seqs = _seqs(n, length)
+    mine = sharding.genome_slice(n, world, rank)
+    eng = _CpuPanelEngine(orc, [seqs[g] for g in mine], k)
+    gi, gj, inter, d = sharding.streamed_all_vs_all(eng, n, world, rank, torch.device("cpu"), panel_genomes=panel)
+    assert len(eng.sets) == len(mine)  # every streamed panel was dropped again
+    ret.put((rank, gi.tolist(), gj.tolist(), [int(x) for x in inter], d.tolist()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,panel", [(2, 2), (3, 1), (4, 3)])
+def test_streamed_panels_over_gloo(orc, world, panel):
+    n, length, k = 9, 12000, 15
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    ret = ctx.Queue()
+    procs = [ctx.Process(target=_stream_worker, args=(r, world, port, n, length, k, panel, ret), daemon=True)
+             for r in range(world)]
+    for p in procs:
+        p.start()
+    got = {}
+    for _ in range(world):
+        rank, gi, gj, inter, d = ret.get(timeout=180)
+        for a, b, i, x in zip(gi, gj, inter, d):
+            assert (a, b) not in got, "pair computed twice"
+            got[(a, b)] = (i, x)
+    for p in procs:
+        p.join(timeout=60)
+    sets = [orc.IntSet(x, k) for x in _seqs(n, length)]
+    want = {(i, j): (sets[i].similarity(sets[j]), sets[i].distance(sets[j])) for i in range(n) for j in range(i + 1, n)}
+    assert got == want

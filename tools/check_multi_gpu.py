@@ -41,6 +41,18 @@ def main():
         ia, ib = sharding.local_pair_ids(id_map, n, first, count)
         gi, gd = eng.pairs(ia, ib)
     ok = np.array_equal(gi, want_i[first:first + count]) and np.array_equal(gd, want_d[first:first + count])
+    # streamed column panels (config-4 path): same numbers without any rank holding every set
+    with gkd.Engine(k=k, device=local) as eng:
+        for g in mine:
+            eng.add(seqs[g])
+        eng.build()
+        si, sj, s_inter, s_dist = sharding.streamed_all_vs_all(eng, n, world, rank, dev, panel_genomes=3)
+        ok = ok and len(eng) == len(mine)
+    lin = np.array([sharding.row_start(int(a), n) + int(b) - int(a) - 1 for a, b in zip(si, sj)], dtype=np.int64)
+    ok = ok and np.array_equal(s_inter, want_i[lin]) and np.array_equal(s_dist, want_d[lin])
+    n_stream = torch.tensor([len(lin)], device=dev)
+    dist.all_reduce(n_stream)
+    ok = ok and int(n_stream) == total
     flag = torch.tensor([1 if ok else 0], device=dev)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:
