@@ -206,14 +206,14 @@ def streamed_all_vs_all(eng, n_genomes: int, world: int, rank: int, device, pane
         n_recv = (len(theirs) + panel_genomes - 1) // panel_genomes if recv_needed else 0
         n_send = (m + panel_genomes - 1) // panel_genomes if send_needed else 0
         for k in range(max(n_recv, n_send)):
-            reqs, send, recv, offs, chunk = [], None, None, None, None
+            ops, send, recv, offs, chunk = [], None, None, None, None
             if k < n_send:
                 lo, hi = k * panel_genomes, min(m, (k + 1) * panel_genomes)
                 parts = [eng.set_tensor(i) for i in range(lo, hi)]
                 send = torch.cat(parts) if parts else torch.empty(0, dtype=torch.int64, device=device)
                 if send.numel() == 0:
                     send = torch.zeros(1, dtype=torch.int64, device=device)
-                reqs.append(dist.isend(send, dst))
+                ops.append(dist.P2POp(dist.isend, send, dst))
             if k < n_recv:
                 chunk = theirs[k * panel_genomes: (k + 1) * panel_genomes]
                 li0 = k * panel_genomes
@@ -221,8 +221,10 @@ def streamed_all_vs_all(eng, n_genomes: int, world: int, rank: int, device, pane
                 offs = np.zeros(len(chunk) + 1, dtype=np.uint64)
                 offs[1:] = np.cumsum(sz)
                 recv = torch.empty(max(int(offs[-1]), 1), dtype=torch.int64, device=device)
-                reqs.append(dist.irecv(recv, src))
-            for r in reqs:
+                ops.append(dist.P2POp(dist.irecv, recv, src))
+            # one NCCL group per sub-panel: every rank's send and receive are posted together, so the
+            # ring cannot deadlock on unmatched point-to-point calls
+            for r in (dist.batch_isend_irecv(ops) if ops else []):
                 r.wait()
             if recv is not None and m > 0:
                 first = eng.import_sets(recv[: int(offs[-1])], offs)
