@@ -148,15 +148,25 @@ def local_pair_ids(id_map: Dict[int, int], n_genomes: int, first: int, count: in
 # Streamed column panels: all-vs-all when the sets do not fit one GPU (BASELINE config 4)
 # ------------------------------------------------------------------------------------------------
 def ring_partners(world: int, rank: int):
-    """Steps s = 1..world//2 of the block ring.  Rank x owns block (x, (x+s) % world); for even
-    worlds the half-way step would pair the same two ranks twice, so only the lower rank computes.
-    Returns [(src, recv_needed, dst, send_needed)]: receive src's panel / send own panel to dst."""
-    out = []
-    for s in range(1, world // 2 + 1):
-        src, dst = (rank + s) % world, (rank - s) % world
-        half = world % 2 == 0 and s == world // 2
-        out.append((src, (not half) or rank < src, dst, (not half) or dst < rank))
-    return out
+    """Steps s = 1..world//2 of the block ring: rank x owns block (x, (x+s) % world) and therefore
+    receives the panel of src = (x+s) % world and sends its own to dst = (x-s) % world.  For even
+    worlds the half-way step pairs the same two ranks in both directions; that block is split between
+    them (see half_step_ranges) so every rank does the same amount of work.
+    Returns [(src, dst, half)]."""
+    return [((rank + s) % world, (rank - s) % world, world % 2 == 0 and s == world // 2)
+            for s in range(1, world // 2 + 1)]
+
+
+def half_step_ranges(m_mine: int, m_partner: int, i_am_lower: bool):
+    """Split of the half-way block X x Y between its two ranks (X = lower rank's genomes, Y = higher's):
+    the lower rank computes X[:h] x Y, the higher rank computes Y x X[h:], h = ceil(|X| / 2).
+    Returns (rows, recv, send) as (start, stop) ranges of local set indices: my rows to use, the
+    partner's sets I receive, my sets I send."""
+    if i_am_lower:
+        h = (m_mine + 1) // 2
+        return (0, h), (0, m_partner), (h, m_mine)
+    h = (m_partner + 1) // 2
+    return (0, m_mine), (h, m_partner), (0, m_mine)
 
 
 def streamed_all_vs_all(eng, n_genomes: int, world: int, rank: int, device, panel_genomes: int = 256):
@@ -200,24 +210,30 @@ def streamed_all_vs_all(eng, n_genomes: int, world: int, rank: int, device, pane
         base = mine[0]
         emit(a.astype(np.int64) + base, b.astype(np.int64) + base, inter, d)
 
-    my_rows = np.arange(m, dtype=np.uint32)
-    for src, recv_needed, dst, send_needed in ring_partners(world, rank):
+    for src, dst, half in ring_partners(world, rank):
         theirs = genome_slice(n_genomes, world, src)
-        n_recv = (len(theirs) + panel_genomes - 1) // panel_genomes if recv_needed else 0
-        n_send = (m + panel_genomes - 1) // panel_genomes if send_needed else 0
+        if half:  # src == dst: the block is split between the two ranks
+            rows, recv_rng, send_rng = half_step_ranges(m, len(theirs), rank < src)
+        else:
+            rows, recv_rng, send_rng = (0, m), (0, len(theirs)), (0, m)
+        my_rows = np.arange(rows[0], rows[1], dtype=np.uint32)
+        n_recv = (recv_rng[1] - recv_rng[0] + panel_genomes - 1) // panel_genomes
+        n_send = (send_rng[1] - send_rng[0] + panel_genomes - 1) // panel_genomes
         for k in range(max(n_recv, n_send)):
             ops, send, recv, offs, chunk = [], None, None, None, None
             if k < n_send:
-                lo, hi = k * panel_genomes, min(m, (k + 1) * panel_genomes)
+                lo = send_rng[0] + k * panel_genomes
+                hi = min(send_rng[1], lo + panel_genomes)
                 parts = [eng.set_tensor(i) for i in range(lo, hi)]
                 send = torch.cat(parts) if parts else torch.empty(0, dtype=torch.int64, device=device)
                 if send.numel() == 0:
                     send = torch.zeros(1, dtype=torch.int64, device=device)
                 ops.append(dist.P2POp(dist.isend, send, dst))
             if k < n_recv:
-                chunk = theirs[k * panel_genomes: (k + 1) * panel_genomes]
-                li0 = k * panel_genomes
-                sz = all_sizes[src][li0: li0 + len(chunk)].astype(np.uint64)
+                li0 = recv_rng[0] + k * panel_genomes
+                li1 = min(recv_rng[1], li0 + panel_genomes)
+                chunk = theirs[li0:li1]
+                sz = all_sizes[src][li0:li1].astype(np.uint64)
                 offs = np.zeros(len(chunk) + 1, dtype=np.uint64)
                 offs[1:] = np.cumsum(sz)
                 recv = torch.empty(max(int(offs[-1]), 1), dtype=torch.int64, device=device)
@@ -226,12 +242,12 @@ def streamed_all_vs_all(eng, n_genomes: int, world: int, rank: int, device, pane
             # ring cannot deadlock on unmatched point-to-point calls
             for r in (dist.batch_isend_irecv(ops) if ops else []):
                 r.wait()
-            if recv is not None and m > 0:
+            if recv is not None and len(my_rows) > 0:
                 first = eng.import_sets(recv[: int(offs[-1])], offs)
                 cols = np.arange(first, first + len(chunk), dtype=np.uint32)
                 inter, d = eng.query_vs_ref(my_rows, cols)
-                rows_g = np.repeat(np.asarray(mine, dtype=np.int64), len(chunk))
-                cols_g = np.tile(np.asarray(chunk, dtype=np.int64), m)
+                rows_g = np.repeat(np.asarray(mine[rows[0]:rows[1]], dtype=np.int64), len(chunk))
+                cols_g = np.tile(np.asarray(chunk, dtype=np.int64), len(my_rows))
                 emit(rows_g, cols_g, inter, d)
                 eng.truncate(m)
             del send, recv

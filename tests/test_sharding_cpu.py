@@ -119,17 +119,23 @@ def test_exchange_and_pair_slices_over_gloo(orc, world):
 
 def test_ring_partners_cover_every_rank_pair_once():
     for world in (1, 2, 3, 4, 5, 8):
-        owned = {}
+        blocks = {}
         for r in range(world):
-            for src, recv_needed, dst, send_needed in sharding.ring_partners(world, r):
-                if recv_needed:
-                    key = frozenset((r, src))
-                    assert key not in owned, (world, key)
-                    owned[key] = r
-                # what I send must be wanted by the receiver, and vice versa
-                back = [p for p in sharding.ring_partners(world, dst) if p[0] == r]
-                assert len(back) == 1 and back[0][1] == send_needed
-        assert len(owned) == world * (world - 1) // 2
+            for src, dst, half in sharding.ring_partners(world, r):
+                assert (not half) or src == dst
+                # my receive is matched by the partner's send in the same step
+                assert any(p[1] == r for p in sharding.ring_partners(world, src))
+                blocks.setdefault(frozenset((r, src)), []).append((r, half))
+        assert len(blocks) == world * (world - 1) // 2
+        for key, owners in blocks.items():
+            # a normal block has one owner; the half-way block of an even ring is shared by its two ranks
+            assert len(owners) == (2 if owners[0][1] else 1), (world, key, owners)
+    for m_lo, m_hi in ((5, 4), (4, 4), (1, 1), (0, 3)):
+        rows_l, recv_l, send_l = sharding.half_step_ranges(m_lo, m_hi, True)
+        rows_h, recv_h, send_h = sharding.half_step_ranges(m_hi, m_lo, False)
+        assert recv_l == send_h and recv_h == send_l
+        # lower covers X[:h] x Y, higher covers Y x X[h:]: together the whole block, no overlap
+        assert (rows_l[1] - rows_l[0]) + (recv_h[1] - recv_h[0]) == m_lo and rows_h == (0, m_hi)
 
 
 class _CpuPanelEngine(_CpuEngine):
