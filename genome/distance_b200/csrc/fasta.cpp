@@ -5,6 +5,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
+#include <sys/stat.h>
 #include <string>
 #include <vector>
 
@@ -27,26 +28,49 @@ int gkd_parse_fasta_file(const char *path, std::vector<char> &storage, std::vect
         return -1;
     }
     storage.clear();
-    char buf[1 << 16];
-    size_t got;
-    while ((got = fread(buf, 1, sizeof(buf), f)) > 0) storage.insert(storage.end(), buf, buf + got);
-    bool bad = ferror(f) != 0;
+    bool bad = false;
+    if (f != stdin) {
+        // size the buffer once and read the file in one call
+        struct stat st;
+        if (fstat(fileno(f), &st) == 0 && st.st_size > 0) {
+            storage.resize((size_t)st.st_size);
+            size_t got = fread(storage.data(), 1, storage.size(), f);
+            storage.resize(got);
+        }
+    }
+    {   // stdin, or whatever is left (size unknown / file grew)
+        char buf[1 << 16];
+        size_t got;
+        while ((got = fread(buf, 1, sizeof(buf), f)) > 0) storage.insert(storage.end(), buf, buf + got);
+        bad = ferror(f) != 0;
+    }
     if (f != stdin) fclose(f);
     if (bad) {
         err = std::string("Read error on ") + path + ".";
         return -1;
     }
     records.clear();
-    const char *p = storage.data();
-    const char *end = p + storage.size();
+    // One pass; the sequence lines of a record are compacted in place (line ends and surrounding
+    // white space dropped) so every record ends up as ONE contiguous piece of `storage`.
+    char *base = storage.data();
+    char *p = base;
+    char *end = base + storage.size();
+    char *w = base;          // write cursor of the compaction (never ahead of the read cursor)
+    char *seq_start = nullptr;
+    auto close_record = [&]() {
+        if (!records.empty() && seq_start && w > seq_start)
+            records.back().lines.push_back(FastaPiece{seq_start, (uint64_t)(w - seq_start)});
+        seq_start = nullptr;
+    };
     while (p < end) {
-        const char *nl = (const char *)memchr(p, '\n', (size_t)(end - p));
-        const char *le = nl ? nl : end;
-        const char *a = p, *b = le;
+        char *nl = (char *)memchr(p, '\n', (size_t)(end - p));
+        char *le = nl ? nl : end;
+        char *a = p, *b = le;
         while (a < b && is_space(*a)) a++;
         while (b > a && is_space(b[-1])) b--;
         if (a < b) {
             if (*a == '>') {
+                close_record();
                 FastaRecord r;
                 const char *h = a + 1;
                 while (h < b && is_space(*h)) h++;
@@ -54,13 +78,18 @@ int gkd_parse_fasta_file(const char *path, std::vector<char> &storage, std::vect
                 while (ws < b && !is_space(*ws)) ws++;
                 r.label.assign(h, ws);
                 while (ws < b && is_space(*ws)) ws++;
-                r.comment.assign(ws, b);
+                r.comment.assign(ws, (const char *)b);
                 records.push_back(std::move(r));
+                w = (nl ? nl + 1 : end);  // the sequence is compacted right after its header line
+                seq_start = w;
             } else if (!records.empty()) {
-                records.back().lines.push_back(FastaPiece{a, (uint64_t)(b - a)});
+                size_t len = (size_t)(b - a);
+                if (w != a) memmove(w, a, len);
+                w += len;
             }
         }
         p = nl ? nl + 1 : end;
     }
+    close_record();
     return 0;
 }
