@@ -99,7 +99,7 @@ __global__ void __launch_bounds__(RADIX_BINS)
 }
 
 // ---- stable scatter of one tile by one digit -------------------------------------------------------
-__global__ void __launch_bounds__(SORT_THREADS)
+__global__ void __launch_bounds__(SORT_THREADS, 4)
     k_radix_scatter(const BatchGenome *__restrict__ genomes, uint32_t n_genomes, const uint64_t *__restrict__ in,
                     uint64_t *__restrict__ out, const uint32_t *__restrict__ tile_offs, int shift, uint32_t dmask) {
     __shared__ uint64_t s_keys[SORT_TILE];
@@ -121,7 +121,7 @@ __global__ void __launch_bounds__(SORT_THREADS)
     // warp w owns tile keys [w*512, (w+1)*512); item i of lane l is key w*512 + i*32 + l, so the
     // (item, lane) order is the input order and the ranking below is stable.
     uint64_t key[SORT_ITEMS];
-    uint32_t rank[SORT_ITEMS];
+    uint16_t rank[SORT_ITEMS];  // < 4096, packed to keep the kernel at 64 registers (4 CTAs per SM)
 #pragma unroll
     for (int i = 0; i < SORT_ITEMS; i++) {
         uint32_t idx = warp * (32 * SORT_ITEMS) + i * 32 + lane;
@@ -134,12 +134,19 @@ __global__ void __launch_bounds__(SORT_THREADS)
 #pragma unroll
     for (int i = 0; i < SORT_ITEMS; i++) {
         const uint32_t d = (uint32_t)(key[i] >> shift) & dmask;
-        const uint32_t peers = __match_any_sync(0xffffffffu, d);
+        // lanes holding the same digit: eight ballots (one per digit bit) instead of MATCH.ANY, whose
+        // latency dominated this kernel (44 % of the stall samples sat on its consumers)
+        uint32_t peers = 0xffffffffu;
+#pragma unroll
+        for (int b = 0; b < RADIX_BITS; b++) {
+            const uint32_t vote = __ballot_sync(0xffffffffu, (d >> b) & 1u);
+            peers &= ((d >> b) & 1u) ? vote : ~vote;
+        }
         const int leader = __ffs(peers) - 1;
         uint32_t prev = 0;
         if (lane == leader) prev = atomicAdd(&s_cnt[warp][d], (uint32_t)__popc(peers));
         prev = __shfl_sync(0xffffffffu, prev, leader);
-        rank[i] = prev + __popc(peers & lt_mask);
+        rank[i] = (uint16_t)(prev + __popc(peers & lt_mask));
     }
     __syncthreads();
     {   // thread d: exclusive scan over warps for digit d, then over digits
