@@ -48,6 +48,8 @@ SYMBOLS = {
     "gkd_set_device_ptr": (_i32, [_vp, _u32, C.POINTER(_vp), _pu64]),
     "gkd_import_set": (_i32, [_vp, _vp, _u64, _pu32]),
     "gkd_import_sets": (_i32, [_vp, _vp, _pu64, _u32, _pu32]),
+    "gkd_save_sets": (_i32, [_vp, C.c_char_p]),
+    "gkd_load_sets": (_i32, [_vp, C.c_char_p, _pu32, _pu32]),
     "gkd_all_vs_all": (_i32, [_vp, _vp, _vp]),
     "gkd_all_vs_all_range": (_i32, [_vp, _u32, _u64, _u64, _vp, _vp]),
     "gkd_query_vs_ref": (_i32, [_vp, _vp, _u32, _vp, _u32, _vp, _vp]),

@@ -917,6 +917,91 @@ int gkd_import_set(gkd_ctx *c, const uint64_t *keys, uint64_t n, uint32_t *out_i
     return gkd_import_sets(c, keys, offsets, 1, out_id);
 }
 
+// .kset layout (little-endian): "GKDKSET1", u32 k, u32 alphabet, u32 n_sets, u32 0; then per set:
+// u64 n_keys, u32 label_len, u32 comment_len, label bytes, comment bytes, n_keys x u64 sorted keys.
+int gkd_save_sets(gkd_ctx *c, const char *path) {
+    CHECK_CTX(c);
+    if (!path) return fail(c, GKD_EINVAL, "gkd_save_sets: null path");
+    CK(cudaSetDevice(c->cfg.device));
+    for (uint32_t i = 0; i < c->genomes.size(); i++) {
+        int rc = check_built(c, i);
+        if (rc) return rc;
+    }
+    FILE *f = fopen(path, "wb");
+    if (!f) return fail(c, GKD_EIO, "Cannot open %s for writing.", path);
+    uint32_t hdr[4] = {(uint32_t)c->k, (uint32_t)c->cfg.alphabet, (uint32_t)c->genomes.size(), 0};
+    bool ok = fwrite("GKDKSET1", 1, 8, f) == 8 && fwrite(hdr, 4, 4, f) == 4;
+    std::vector<uint64_t> host;
+    for (uint32_t i = 0; ok && i < c->genomes.size(); i++) {
+        const GenomeRec &g = c->genomes[i];
+        uint64_t n = g.desc.n;
+        uint32_t ll[2] = {(uint32_t)g.label.size(), (uint32_t)g.comment.size()};
+        host.resize(n);
+        if (n) {
+            cudaError_t e = cudaMemcpyAsync(host.data(), g.desc.keys, n * 8, cudaMemcpyDeviceToHost, c->stream);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+            if (e != cudaSuccess) {
+                fclose(f);
+                c->poisoned = true;
+                return fail(c, GKD_ECUDA, "gkd_save_sets: %s", cudaGetErrorString(e));
+            }
+        }
+        ok = fwrite(&n, 8, 1, f) == 1 && fwrite(ll, 4, 2, f) == 2 &&
+             fwrite(g.label.data(), 1, ll[0], f) == ll[0] && fwrite(g.comment.data(), 1, ll[1], f) == ll[1] &&
+             fwrite(host.data(), 8, n, f) == n;
+    }
+    ok = (fclose(f) == 0) && ok;
+    return ok ? GKD_OK : fail(c, GKD_EIO, "Write error on %s.", path);
+}
+
+int gkd_load_sets(gkd_ctx *c, const char *path, uint32_t *first_id, uint32_t *n_loaded) {
+    CHECK_CTX(c);
+    if (!path) return fail(c, GKD_EINVAL, "gkd_load_sets: null path");
+    FILE *f = fopen(path, "rb");
+    if (!f) return fail(c, GKD_EIO, "Input file %s is not found or unreadable.", path);
+    char magic[8];
+    uint32_t hdr[4];
+    if (fread(magic, 1, 8, f) != 8 || memcmp(magic, "GKDKSET1", 8) != 0 || fread(hdr, 4, 4, f) != 4) {
+        fclose(f);
+        return fail(c, GKD_EIO, "%s is not a .kset file.", path);
+    }
+    if ((int)hdr[0] != c->k || (int)hdr[1] != c->cfg.alphabet) {
+        fclose(f);
+        return fail(c, GKD_EINVAL, "%s holds k=%u alphabet=%u sets; this context is k=%d alphabet=%d", path, hdr[0], hdr[1],
+                    c->k, c->cfg.alphabet);
+    }
+    const uint32_t n = hdr[2];
+    std::vector<uint64_t> keys, offsets(1, 0);
+    std::vector<std::string> labels(n), comments(n);
+    bool ok = true;
+    for (uint32_t i = 0; ok && i < n; i++) {
+        uint64_t nk;
+        uint32_t ll[2];
+        ok = fread(&nk, 8, 1, f) == 1 && fread(ll, 4, 2, f) == 2 && nk < 0xFFFF0000ull && ll[0] < (1u << 20) && ll[1] < (1u << 20);
+        if (!ok) break;
+        labels[i].resize(ll[0]);
+        comments[i].resize(ll[1]);
+        ok = fread(&labels[i][0], 1, ll[0], f) == ll[0] && fread(&comments[i][0], 1, ll[1], f) == ll[1];
+        if (!ok) break;
+        size_t at = keys.size();
+        keys.resize(at + nk);
+        ok = fread(keys.data() + at, 8, nk, f) == nk;
+        offsets.push_back(keys.size());
+    }
+    fclose(f);
+    if (!ok) return fail(c, GKD_EIO, "%s is truncated or corrupt.", path);
+    uint32_t first = 0;
+    int rc = gkd_import_sets(c, keys.data(), offsets.data(), n, &first);
+    if (rc) return rc;
+    for (uint32_t i = 0; i < n; i++) {
+        c->genomes[first + i].label = labels[i];
+        c->genomes[first + i].comment = comments[i];
+    }
+    if (first_id) *first_id = first;
+    if (n_loaded) *n_loaded = n;
+    return GKD_OK;
+}
+
 int gkd_all_vs_all(gkd_ctx *c, uint64_t *inter, double *dist) {
     CHECK_CTX(c);
     CK(cudaSetDevice(c->cfg.device));

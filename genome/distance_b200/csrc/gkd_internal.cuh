@@ -42,8 +42,8 @@ constexpr char STREAM_SEPARATOR = 0;  // byte written between contigs in the sta
 constexpr int SORT_THREADS = 256;
 constexpr int SORT_ITEMS = 16;
 constexpr int SORT_TILE = SORT_THREADS * SORT_ITEMS;  // 4096 keys per tile
-constexpr int RADIX_BITS = 8;
-constexpr int RADIX_BINS = 1 << RADIX_BITS;
+constexpr int RADIX_BITS = 8;               // widest digit of a pass; widths are evened out (42-bit keys: six 7-bit passes)
+constexpr int RADIX_BINS = 1 << RADIX_BITS;  // row stride of the per-tile histogram table
 
 // Encode geometry (tile == sort tile so one table of tiles serves both)
 constexpr int ENC_THREADS = 256;

@@ -8,7 +8,9 @@
 //
 // Bound: HBM.  Ideal algorithmic bytes are 16 B/key (read once, write once); this LSD implementation
 // physically moves 24 B/key per pass (8 B histogram read + 8 B read + 8 B write) over
-// ceil(key_bits / 8) passes, plus 8 B (count) + 16 B (compact write) for the unique pass.
+// ceil(key_bits / 8) passes with evened-out digit widths (42-bit keys: six 7-bit passes, which keeps
+// the per-digit write runs of a 4096-key tile at 256 B; 9-bit digits / 5 passes measured no faster
+// because the runs shrink to 64 B), plus 8 B (count) + 16 B (compact write) for the unique pass.
 #include "gkd_internal.cuh"
 
 namespace gkd {
@@ -54,8 +56,8 @@ __global__ void __launch_bounds__(SORT_THREADS)
 }
 
 // ---- block-wide exclusive scan of one value per thread (256 threads) -----------------------------
-template <typename T>
-__device__ __forceinline__ T block_exclusive_scan(T v, T *s_warp /* [SORT_WARPS] */, T &total) {
+template <typename T, int NW = SORT_WARPS>
+__device__ __forceinline__ T block_exclusive_scan(T v, T *s_warp /* [NW] */, T &total) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     T incl = v;
 #pragma unroll
@@ -67,7 +69,7 @@ __device__ __forceinline__ T block_exclusive_scan(T v, T *s_warp /* [SORT_WARPS]
     __syncthreads();
     T base = 0, tot = 0;
 #pragma unroll
-    for (int w = 0; w < SORT_WARPS; w++) {
+    for (int w = 0; w < NW; w++) {
         T c = s_warp[w];
         if (w < warp) base += c;
         tot += c;
@@ -80,7 +82,7 @@ __device__ __forceinline__ T block_exclusive_scan(T v, T *s_warp /* [SORT_WARPS]
 // ---- per-genome scan of the tile histograms: (digit-major, tile-minor) exclusive offsets ----------
 __global__ void __launch_bounds__(RADIX_BINS)
     k_radix_scan(const BatchGenome *__restrict__ genomes, uint32_t *__restrict__ tile_hist) {
-    __shared__ uint32_t s_warp[SORT_WARPS];
+    __shared__ uint32_t s_warp[RADIX_BINS / 32];
     const BatchGenome G = genomes[blockIdx.x];
     if (G.n_tiles == 0) return;
     const int d = threadIdx.x;
@@ -93,7 +95,7 @@ __global__ void __launch_bounds__(RADIX_BINS)
         run += c;
     }
     uint32_t total;
-    uint32_t base = block_exclusive_scan<uint32_t>(run, s_warp, total);
+    uint32_t base = block_exclusive_scan<uint32_t, RADIX_BINS / 32>(run, s_warp, total);
 #pragma unroll 8
     for (uint32_t t = 0; t < G.n_tiles; t++) col[(size_t)t * RADIX_BINS] += base;
 }
@@ -102,7 +104,7 @@ __global__ void __launch_bounds__(RADIX_BINS)
 __global__ void __launch_bounds__(SORT_THREADS, 4)
     k_radix_scatter(const BatchGenome *__restrict__ genomes, uint32_t n_genomes, const uint64_t *__restrict__ in,
                     uint64_t *__restrict__ out, const uint32_t *__restrict__ tile_offs, int shift, uint32_t dmask) {
-    __shared__ uint64_t s_keys[SORT_TILE];
+    extern __shared__ __align__(16) uint64_t s_keys[];  // SORT_TILE keys (dynamic: static smem is at its 48 KiB cap)
     __shared__ uint32_t s_cnt[SORT_WARPS][RADIX_BINS];
     __shared__ uint32_t s_dstart[RADIX_BINS];
     __shared__ uint32_t s_goff[RADIX_BINS];
@@ -149,19 +151,31 @@ __global__ void __launch_bounds__(SORT_THREADS, 4)
         rank[i] = (uint16_t)(prev + __popc(peers & lt_mask));
     }
     __syncthreads();
-    {   // thread d: exclusive scan over warps for digit d, then over digits
-        const int d = threadIdx.x;
-        uint32_t sum = 0;
+    {   // per digit: exclusive scan over warps, then over digits
+        constexpr int DPT = (RADIX_BINS + SORT_THREADS - 1) / SORT_THREADS;  // digits per thread
+        static_assert(DPT == 1 || DPT == 2, "digit scan handles up to 2 digits per thread");
+        uint32_t sum[2] = {0, 0};
 #pragma unroll
-        for (int w = 0; w < SORT_WARPS; w++) {
-            uint32_t c = s_cnt[w][d];
-            s_cnt[w][d] = sum;
-            sum += c;
+        for (int h = 0; h < DPT; h++) {
+            const int d = threadIdx.x + h * SORT_THREADS;
+            uint32_t acc = 0;
+#pragma unroll
+            for (int w = 0; w < SORT_WARPS; w++) {
+                uint32_t c = s_cnt[w][d];
+                s_cnt[w][d] = acc;
+                acc += c;
+            }
+            sum[h] = acc;
         }
-        uint32_t total;
-        uint32_t start = block_exclusive_scan<uint32_t>(sum, s_warp, total);
-        s_dstart[d] = start;
-        s_goff[d] = tile_offs[(size_t)blockIdx.x * RADIX_BINS + d];
+        uint32_t total0, total1;
+        const uint32_t start0 = block_exclusive_scan<uint32_t>(sum[0], s_warp, total0);
+        s_dstart[threadIdx.x] = start0;
+        s_goff[threadIdx.x] = tile_offs[(size_t)blockIdx.x * RADIX_BINS + threadIdx.x];
+        if (DPT == 2) {
+            const uint32_t start1 = block_exclusive_scan<uint32_t>(sum[1], s_warp, total1) + total0;
+            s_dstart[threadIdx.x + SORT_THREADS] = start1;
+            s_goff[threadIdx.x + SORT_THREADS] = tile_offs[(size_t)blockIdx.x * RADIX_BINS + threadIdx.x + SORT_THREADS];
+        }
     }
     __syncthreads();
 #pragma unroll
@@ -179,21 +193,34 @@ __global__ void __launch_bounds__(SORT_THREADS, 4)
     }
 }
 
+static bool g_scatter_configured = false;
+
 cudaError_t launch_sort(const BatchGenome *genomes, const SortPlan &plan, uint64_t **sorted_out, uint32_t *passes,
                         cudaStream_t s) {
     uint64_t *src = plan.keys_a, *dst = plan.keys_b;
     uint32_t np = 0;
-    if (plan.n_tiles > 0) {
-        for (int shift = 0; shift < plan.key_bits; shift += RADIX_BITS) {
-            int bits = plan.key_bits - shift < RADIX_BITS ? plan.key_bits - shift : RADIX_BITS;
-            uint32_t dmask = (1u << bits) - 1u;
+    if (!g_scatter_configured) {
+        cudaError_t e = cudaFuncSetAttribute(k_radix_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)(SORT_TILE * sizeof(uint64_t)));
+        if (e != cudaSuccess) return e;
+        g_scatter_configured = true;
+    }
+    if (plan.n_tiles > 0 && plan.key_bits > 0) {
+        // fewest passes of at most RADIX_BITS bits, widths as even as possible (42 bits -> 9,9,8,8,8)
+        const int n_pass = (plan.key_bits + RADIX_BITS - 1) / RADIX_BITS;
+        const int base = plan.key_bits / n_pass, extra = plan.key_bits % n_pass;
+        int shift = 0;
+        for (int p = 0; p < n_pass; p++) {
+            const int bits = base + (p >= n_pass - extra ? 1 : 0);
+            const uint32_t dmask = (1u << bits) - 1u;
             k_radix_hist<<<plan.n_tiles, SORT_THREADS, 0, s>>>(genomes, plan.n_genomes, src, plan.tile_hist, shift, dmask);
             k_radix_scan<<<plan.n_genomes, RADIX_BINS, 0, s>>>(genomes, plan.tile_hist);
-            k_radix_scatter<<<plan.n_tiles, SORT_THREADS, 0, s>>>(genomes, plan.n_genomes, src, dst, plan.tile_hist, shift,
-                                                                  dmask);
+            k_radix_scatter<<<plan.n_tiles, SORT_THREADS, SORT_TILE * sizeof(uint64_t), s>>>(
+                genomes, plan.n_genomes, src, dst, plan.tile_hist, shift, dmask);
             uint64_t *t = src;
             src = dst;
             dst = t;
+            shift += bits;
             np++;
         }
     }

@@ -236,6 +236,16 @@ class Engine:
         """cudaStream_t of this context (wrap with torch.cuda.ExternalStream to time on it)"""
         return self._L.gkd_stream(self._h) or 0
 
+    def save_sets(self, path: str):
+        """write every set (with label and comment) to a .kset cache file"""
+        self._ck(self._L.gkd_save_sets(self._h, path.encode()))
+
+    def load_sets(self, path: str) -> Tuple[int, int]:
+        """append the sets of a .kset cache file; returns (first id, count)"""
+        first, n = C.c_uint32(), C.c_uint32()
+        self._ck(self._L.gkd_load_sets(self._h, path.encode(), C.byref(first), C.byref(n)))
+        return first.value, n.value
+
     def truncate(self, n_keep: int):
         """drop the sets with id >= n_keep (a streamed panel) and recycle their arena"""
         self._ck(self._L.gkd_truncate(self._h, n_keep))

@@ -133,6 +133,12 @@ int gkd_import_set(gkd_ctx *ctx, const uint64_t *keys, uint64_t n, uint32_t *out
  * synchronisation; ids first_id .. first_id+n_sets-1 are assigned in order. */
 int gkd_import_sets(gkd_ctx *ctx, const uint64_t *keys, const uint64_t *offsets, uint32_t n_sets, uint32_t *first_id);
 
+/* persisted sorted-set cache (".kset"): every set of the context with its label and comment, so a
+ * reference panel is built once.  Loading appends the sets as new ids and
+ * fails with GKD_EINVAL if the file was written for a different k / alphabet. */
+int gkd_save_sets(gkd_ctx *ctx, const char *path);
+int gkd_load_sets(gkd_ctx *ctx, const char *path, uint32_t *first_id, uint32_t *n_loaded);
+
 /* ---- distances: kernels 4 + 5 --------------------------------------------------------------- */
 /* All pairs i<j in id order, row-major strict upper triangle of length N*(N-1)/2
  * (FastaDistanceProcessor.runReporter/computePairs :141-162,174-194).  inter receives the reference's

@@ -359,3 +359,34 @@ def test_many_small_sequences_all_vs_all(orc, k, alpha):
     oi, od = orc.fasta_dist(seqs, k, alphabet=oal, batch=20, threads=0, mode=1)
     assert np.array_equal(gi, oi) and np.array_equal(gd, od)
     assert (gd < 0.5).any() and (gd == 1.0).any()
+
+
+def test_kset_cache_and_truncate(orc, tmp_path):
+    """persisted sorted-set cache (.kset) round trip, and dropping a streamed panel with truncate"""
+    seqs = _np_family(31, 6, 40000, [0.01, 0.05])
+    path = str(tmp_path / "panel.kset")
+    with gkd.Engine(k=20) as e:  # even K: palindrome lists must survive the round trip
+        for s in seqs:
+            e.add(s)
+        e.build()
+        want_i, want_d = e.all_vs_all()
+        sizes = [e.set_size(i) for i in range(len(seqs))]
+        e.save_sets(path)
+    with gkd.Engine(k=20) as f:
+        assert f.load_sets(path) == (0, len(seqs))
+        assert [f.set_size(i) for i in range(len(seqs))] == sizes
+        gi, gd = f.all_vs_all()
+        assert np.array_equal(gi, want_i) and np.array_equal(gd, want_d)
+        # append the panel again, use it, drop it: ids below the cut stay valid
+        first, n = f.load_sets(path)
+        assert (first, n) == (len(seqs), len(seqs))
+        qi, qd = f.query_vs_ref(list(range(len(seqs))), list(range(first, first + n)))
+        assert all(qd[i, i] == 0.0 for i in range(len(seqs)))
+        f.truncate(len(seqs))
+        assert len(f) == len(seqs)
+        gi2, gd2 = f.all_vs_all()
+        assert np.array_equal(gi2, want_i) and np.array_equal(gd2, want_d)
+    with gkd.Engine(k=21) as g:
+        with pytest.raises(gkd.GkdError) as err:
+            g.load_sets(path)
+        assert err.value.code == -1
