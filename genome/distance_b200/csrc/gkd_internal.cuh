@@ -6,10 +6,6 @@
 
 #include "gkd.h"
 
-#ifndef __CUDA_ARCH_LIST__
-#define __CUDA_ARCH_LIST__ 1000
-#endif
-
 namespace gkd {
 
 // ------------------------------------------------------------------------------------------------
@@ -126,6 +122,25 @@ cudaError_t launch_epilogue(const SetDesc *sets, PairSource src, const uint32_t 
 cudaError_t launch_synth(char *dst, uint64_t len, uint64_t seed, uint32_t family, uint32_t member, double rate,
                          int protein, cudaStream_t s);
 void synth_host(char *dst, uint64_t len, uint64_t seed, uint32_t family, uint32_t member, double rate, int protein);
+
+#ifdef __CUDACC__
+// which genome of a batch owns tile `tile` (tile_first is ascending)
+__device__ __forceinline__ uint32_t find_genome(const BatchGenome *__restrict__ g, uint32_t n, uint32_t tile) {
+    uint32_t lo = 0, hi = n;
+    while (hi - lo > 1) {
+        uint32_t mid = (lo + hi) >> 1;
+        if (g[mid].tile_first <= tile) lo = mid;
+        else hi = mid;
+    }
+    return lo;
+}
+
+// reverse the order of the 32 two-bit groups of x (base order of a packed k-mer)
+__device__ __forceinline__ uint64_t reverse_pairs(uint64_t x) {
+    uint64_t y = __brevll(x);
+    return ((y >> 1) & 0x5555555555555555ull) | ((y & 0x5555555555555555ull) << 1);
+}
+#endif
 
 // decode the linear index of the row-major strict upper triangle of an n x n matrix
 __host__ __device__ inline void upper_pair(uint64_t t, uint32_t n, uint32_t &i, uint32_t &j) {

@@ -118,22 +118,6 @@ cudaError_t launch_pack_prot(const char *text, uint64_t n_pos, uint8_t *codes, u
 // ------------------------------------------------------------------------------------------------
 // kernel 2: rolling canonical encode
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint64_t reverse_pairs(uint64_t x) {
-    uint64_t y = __brevll(x);
-    return ((y >> 1) & 0x5555555555555555ull) | ((y & 0x5555555555555555ull) << 1);
-}
-
-// which genome of the batch owns tile `tile` (tile_first is ascending)
-__device__ __forceinline__ uint32_t find_genome(const BatchGenome *__restrict__ g, uint32_t n, uint32_t tile) {
-    uint32_t lo = 0, hi = n;
-    while (hi - lo > 1) {
-        uint32_t mid = (lo + hi) >> 1;
-        if (g[mid].tile_first <= tile) lo = mid;
-        else hi = mid;
-    }
-    return lo;
-}
-
 constexpr int ENC_STRIDE = ENC_PER_THREAD + 1;  // smem padding: conflict-free 64-bit stores
 
 template <int ALPHA>

@@ -15,16 +15,6 @@
 
 namespace gkd {
 
-__device__ __forceinline__ uint32_t find_genome_s(const BatchGenome *__restrict__ g, uint32_t n, uint32_t tile) {
-    uint32_t lo = 0, hi = n;
-    while (hi - lo > 1) {
-        uint32_t mid = (lo + hi) >> 1;
-        if (g[mid].tile_first <= tile) lo = mid;
-        else hi = mid;
-    }
-    return lo;
-}
-
 constexpr int SORT_WARPS = SORT_THREADS / 32;
 
 // ---- per-tile digit histogram -------------------------------------------------------------------
@@ -33,7 +23,7 @@ __global__ void __launch_bounds__(SORT_THREADS)
                  uint32_t *__restrict__ tile_hist, int shift, uint32_t dmask) {
     __shared__ uint32_t s_hist[SORT_WARPS][RADIX_BINS];
     __shared__ uint32_t s_g;
-    if (threadIdx.x == 0) s_g = find_genome_s(genomes, n_genomes, blockIdx.x);
+    if (threadIdx.x == 0) s_g = find_genome(genomes, n_genomes, blockIdx.x);
     for (int i = threadIdx.x; i < SORT_WARPS * RADIX_BINS; i += SORT_THREADS) (&s_hist[0][0])[i] = 0;
     __syncthreads();
     const BatchGenome G = genomes[s_g];
@@ -110,7 +100,7 @@ __global__ void __launch_bounds__(SORT_THREADS, 4)
     __shared__ uint32_t s_goff[RADIX_BINS];
     __shared__ uint32_t s_warp[SORT_WARPS];
     __shared__ uint32_t s_g;
-    if (threadIdx.x == 0) s_g = find_genome_s(genomes, n_genomes, blockIdx.x);
+    if (threadIdx.x == 0) s_g = find_genome(genomes, n_genomes, blockIdx.x);
     for (int i = threadIdx.x; i < SORT_WARPS * RADIX_BINS; i += SORT_THREADS) (&s_cnt[0][0])[i] = 0;
     __syncthreads();
     const BatchGenome G = genomes[s_g];
@@ -230,11 +220,6 @@ cudaError_t launch_sort(const BatchGenome *genomes, const SortPlan &plan, uint64
 }
 
 // ---- unique / compaction ---------------------------------------------------------------------------
-__device__ __forceinline__ uint64_t reverse_pairs_u(uint64_t x) {
-    uint64_t y = __brevll(x);
-    return ((y >> 1) & 0x5555555555555555ull) | ((y & 0x5555555555555555ull) << 1);
-}
-
 // packed flags of one sorted position: low word = "first occurrence of a real key", high word = "and
 // it is its own reverse complement"
 __device__ __forceinline__ uint64_t unique_flags(const uint64_t *__restrict__ sorted, uint32_t idx, uint32_t n,
@@ -250,7 +235,7 @@ __device__ __forceinline__ uint64_t unique_flags(const uint64_t *__restrict__ so
     uint64_t f = 1;
     if (check_pal) {
         uint64_t kmask = (k >= 32) ? ~0ull : ((1ull << (2 * k)) - 1);
-        uint64_t rc = (~(reverse_pairs_u(kx) >> (64 - 2 * k))) & kmask;
+        uint64_t rc = (~(reverse_pairs(kx) >> (64 - 2 * k))) & kmask;
         if (rc == kx) f |= 1ull << 32;
     }
     return f;
@@ -261,7 +246,7 @@ __global__ void __launch_bounds__(SORT_THREADS)
                    uint64_t *__restrict__ tile_uniq, int check_pal, int k) {
     __shared__ uint64_t s_warp[SORT_WARPS];
     __shared__ uint32_t s_g;
-    if (threadIdx.x == 0) s_g = find_genome_s(genomes, n_genomes, blockIdx.x);
+    if (threadIdx.x == 0) s_g = find_genome(genomes, n_genomes, blockIdx.x);
     __syncthreads();
     const BatchGenome G = genomes[s_g];
     const uint32_t slot0 = (blockIdx.x - G.tile_first) * SORT_TILE;
@@ -299,7 +284,7 @@ __global__ void __launch_bounds__(SORT_THREADS)
                    const uint64_t *__restrict__ tile_uniq, const UniqueDst *__restrict__ dst, int check_pal, int k) {
     __shared__ uint64_t s_warp[SORT_WARPS];
     __shared__ uint32_t s_g;
-    if (threadIdx.x == 0) s_g = find_genome_s(genomes, n_genomes, blockIdx.x);
+    if (threadIdx.x == 0) s_g = find_genome(genomes, n_genomes, blockIdx.x);
     __syncthreads();
     const BatchGenome G = genomes[s_g];
     const UniqueDst D = dst[s_g];

@@ -3,7 +3,7 @@ sharding.  The product is libgkd.so; nothing here computes."""
 from __future__ import annotations
 
 import ctypes as C
-from typing import Iterable, List, Optional, Sequence, Tuple
+from typing import List, Sequence, Tuple
 
 import numpy as np
 

@@ -29,7 +29,7 @@ def build(force: bool = False) -> str:
     """Compile the C oracle (gcc, seconds)."""
     src = os.path.join(_HERE, "gkd_oracle.c")
     if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < os.path.getmtime(src):
-        subprocess.check_call(["make", "-C", _HERE, "-s", "-B" if force else "-s"])
+        subprocess.check_call(["make", "-C", _HERE, "-s"] + (["-B"] if force else []))
     return _LIB_PATH
 
 
