@@ -390,3 +390,36 @@ def test_kset_cache_and_truncate(orc, tmp_path):
         with pytest.raises(gkd.GkdError) as err:
             g.load_sets(path)
         assert err.value.code == -1
+
+
+def test_fuzz_against_oracle(orc):
+    """Randomised differential test: random alphabets, K, contig structures and sizes through the
+    C ABI versus the literal Python-set restatement (the most direct reading of HashSet<String>)."""
+    rng = random.Random(20261018)
+    for trial in range(40):
+        prot = trial % 4 == 3
+        k = rng.randint(1, 8) if prot else rng.choice([2, 3, 4, 5, 6, 7, 9, 12, 13, 16, 17, 21, 24, 31, 32])
+        letters = "ACDEFGHIKLMNPQRSTVWYX" if prot else rng.choice(["acgt", "ACGTacgt", "acgtn", "ac", "acgtRYN"])
+        n_genomes = rng.randint(2, 6)
+        base = [_rand_dna(rng, rng.randint(0, 400), letters) for _ in range(rng.randint(1, 4))]
+        genomes = []
+        for g in range(n_genomes):
+            if rng.random() < 0.6:
+                genomes.append([_mutate(rng, c, rng.choice([0.0, 0.02, 0.2]), letters) for c in base])
+            else:
+                genomes.append([_rand_dna(rng, rng.randint(0, 300), letters) for _ in range(rng.randint(0, 3))])
+        al, oal = (gkd.PROT, orc.PROT) if prot else (gkd.DNA, orc.DNA)
+        with gkd.Engine(k=k, alphabet=al) as e:
+            for g in genomes:
+                e.add(g)
+            e.build()
+            gi, gd = e.all_vs_all()
+            sizes = [e.set_size(i)[0] for i in range(n_genomes)]
+        psets = [orc.py_kmer_set(g, k, oal) for g in genomes]
+        assert sizes == [len(s) for s in psets], (trial, k, letters)
+        t = 0
+        for i in range(n_genomes):
+            for j in range(i + 1, n_genomes):
+                inter, dist = orc.py_distance(psets[i], psets[j])
+                assert (int(gi[t]), gd[t]) == (inter, dist), (trial, k, letters, i, j)
+                t += 1
