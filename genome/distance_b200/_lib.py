@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libgkd.so")
+LIB_PATH = os.environ.get("GKD_LIB") or os.path.join(_HERE, "libgkd.so")  # GKD_LIB: tuning builds only
 
 GKD_OK, GKD_EINVAL, GKD_EIO, GKD_ENOMEM, GKD_ECUDA, GKD_ESTATE = 0, -1, -2, -3, -4, -5
 DNA, PROT, RNA = 0, 1, 2

@@ -461,13 +461,14 @@ int run_pairs(gkd_ctx *c, const HostPairs &hp, uint64_t *inter, double *dist) {
     c->m.intersect_ms = c->m.epilogue_ms = 0;
 
     // validate ids, gather sizes for the segmenting decision and the byte accounting
-    uint64_t max_n = 0;
+    uint64_t max_n = 0, min_n = UINT64_MAX;
     long double sum_bytes = 0;
     auto size_of = [&](uint32_t id) -> uint64_t { return c->genomes[id].desc.n; };
     if (hp.mode == PAIRS_UPPER) {
         for (uint32_t i = 0; i < hp.n; i++) {
             if ((rc = check_built(c, i))) return rc;
             max_n = std::max<uint64_t>(max_n, size_of(i));
+            if (size_of(i)) min_n = std::min<uint64_t>(min_n, size_of(i));
         }
         // bytes of the requested range, row by row
         uint32_t i0 = 0, j0 = 1;
@@ -486,11 +487,13 @@ int run_pairs(gkd_ctx *c, const HostPairs &hp, uint64_t *inter, double *dist) {
             if ((rc = check_built(c, hp.a[i]))) return rc;
             sq += size_of(hp.a[i]);
             max_n = std::max<uint64_t>(max_n, size_of(hp.a[i]));
+            if (size_of(hp.a[i])) min_n = std::min<uint64_t>(min_n, size_of(hp.a[i]));
         }
         for (uint32_t i = 0; i < hp.nb; i++) {
             if ((rc = check_built(c, hp.b[i]))) return rc;
             sr += size_of(hp.b[i]);
             max_n = std::max<uint64_t>(max_n, size_of(hp.b[i]));
+            if (size_of(hp.b[i])) min_n = std::min<uint64_t>(min_n, size_of(hp.b[i]));
         }
         sum_bytes = 8.0L * ((long double)sq * hp.nb + (long double)sr * hp.na);
     } else {
@@ -500,6 +503,8 @@ int run_pairs(gkd_ctx *c, const HostPairs &hp, uint64_t *inter, double *dist) {
             uint64_t s = size_of(hp.a[t]) + size_of(hp.b[t]);
             sum_bytes += 8.0L * s;
             max_n = std::max<uint64_t>(max_n, std::max(size_of(hp.a[t]), size_of(hp.b[t])));
+            if (size_of(hp.a[t])) min_n = std::min<uint64_t>(min_n, size_of(hp.a[t]));
+            if (size_of(hp.b[t])) min_n = std::min<uint64_t>(min_n, size_of(hp.b[t]));
         }
     }
     c->m.intersect_bytes = (uint64_t)sum_bytes;
@@ -509,12 +514,13 @@ int run_pairs(gkd_ctx *c, const HostPairs &hp, uint64_t *inter, double *dist) {
     uint64_t max_pal = 0;
     if (need_pal)
         for (auto &g : c->genomes) max_pal = std::max<uint64_t>(max_pal, g.desc.n_pal);
+    const int algo = intersect_select(min_n == UINT64_MAX ? 0 : min_n, max_n);
     const bool small_main = c->cfg.segment_keys == 0 && max_n <= intersect_small_max_keys();
     const bool small_pal = max_pal <= intersect_small_max_keys();
 
     // merge-path segmenting: whole pairs when there are enough of them to fill the machine
     const uint64_t max_l = std::max<uint64_t>(2 * max_n, 1);
-    const uint64_t target_items = (uint64_t)c->n_sms * 3 * 8;
+    const uint64_t target_items = (uint64_t)c->n_sms * intersect_items_per_sm(algo);
     uint64_t seg = c->cfg.segment_keys;
     if (seg == 0) {
         if (hp.count >= target_items) seg = max_l;
@@ -572,7 +578,7 @@ int run_pairs(gkd_ctx *c, const HostPairs &hp, uint64_t *inter, double *dist) {
             CK(launch_intersect_small((const SetDesc *)c->d_sets.p, src, 0, (uint32_t *)c->counts.p, c->n_sms, c->stream));
         else
             CK(launch_intersect((const SetDesc *)c->d_sets.p, src, 0, (uint32_t)seg, max_segs, (uint32_t *)c->counts.p,
-                                (unsigned long long *)c->work_counter.p, c->n_sms, c->stream));
+                                (unsigned long long *)c->work_counter.p, c->n_sms, algo, c->stream));
         CK(cudaEventRecord(c->ev[5], c->stream));
         c->m.launches++;
         c->m.intersect_launches++;
@@ -583,7 +589,7 @@ int run_pairs(gkd_ctx *c, const HostPairs &hp, uint64_t *inter, double *dist) {
             else
                 CK(launch_intersect((const SetDesc *)c->d_sets.p, src, 1, (uint32_t)seg, max_segs,
                                     (uint32_t *)c->pal_counts.p, (unsigned long long *)c->work_counter.p, c->n_sms,
-                                    c->stream));
+                                    algo, c->stream));
             c->m.launches++;
         }
         CK(cudaEventRecord(c->ev[6], c->stream));

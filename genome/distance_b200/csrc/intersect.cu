@@ -71,6 +71,19 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         if (++spins > (1u << 24)) __trap();  // a lost copy must not hang the GPU
     } while (!done);
 }
+__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return done != 0;
+}
 __device__ __forceinline__ uint64_t lds64(uint32_t addr) {
     uint64_t v;
     asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(addr));
@@ -113,6 +126,15 @@ __device__ __forceinline__ uint32_t diag_search_global(const uint64_t *__restric
     }
     return lo;
 }
+
+constexpr int WK_WARPS = 8;  // warp-cooperative variant: warps per CTA
+#ifndef GKD_WK_CTAS
+#define GKD_WK_CTAS 3
+#endif
+#ifndef GKD_WK_BLK
+#define GKD_WK_BLK 256
+#endif
+constexpr int WK_CTAS = GKD_WK_CTAS;  // CTAs per SM
 
 // Kernel configuration: THREADS x VT keys per round, ring of NBLK blocks per input.
 template <int THREADS_, int VT_, int NBLK_, int CTAS_>
@@ -371,6 +393,7 @@ constexpr int N_CFG = 6;
 constexpr int DEFAULT_CFG = 0;
 
 static int g_cfg = DEFAULT_CFG;
+static int g_algo_mode = 2;  // GKD_ISECT_ALGO: 0 = cta, 1 = warp, 2 = auto (by size balance, see intersect_select)
 
 static int pick_cfg() {
     const char *e = getenv("GKD_ISECT_CFG");
@@ -382,6 +405,10 @@ static int pick_cfg() {
 
 cudaError_t intersect_configure() {
     g_cfg = pick_cfg();
+    {
+        const char *a = getenv("GKD_ISECT_ALGO");
+        g_algo_mode = !a ? 2 : (a[0] == 'w' ? 1 : (a[0] == 'c' ? 0 : 2));
+    }
     cudaError_t e;
 #define X(i, C) \
     if ((e = cudaFuncSetAttribute(k_intersect<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM))) return e;
@@ -389,6 +416,18 @@ cudaError_t intersect_configure() {
 #undef X
     return cudaSuccess;
 }
+
+// The warp-cooperative kernel advances both inputs by the keys below min(a[31], b[31]) per step, which
+// is efficient when the two sets have similar key density; a pair of very different sizes makes it
+// crawl through the denser set 32 keys at a time, where the CTA kernel's merge-path rounds stay
+// balanced.  Auto mode therefore takes the warp kernel only when the participating sets are within
+// a factor of four in size.
+int intersect_select(uint64_t min_keys, uint64_t max_keys) {
+    if (g_algo_mode != 2) return g_algo_mode;
+    return (min_keys > 0 && max_keys <= 4 * min_keys) ? 1 : 0;
+}
+
+int intersect_items_per_sm(int algo) { return algo ? WK_CTAS * WK_WARPS * 6 : 3 * 8; }
 
 int intersect_min_segment() {
 #define X(i, C) \
@@ -408,16 +447,265 @@ static cudaError_t launch_cfg(const SetDesc *sets, PairSource src, int use_pal, 
     return cudaGetLastError();
 }
 
+static cudaError_t launch_warp(const SetDesc *sets, PairSource src, int use_pal, uint32_t seg_keys, uint32_t max_segs,
+                               uint32_t *counts, unsigned long long *work_counter, int n_sms, cudaStream_t s);
+
 cudaError_t launch_intersect(const SetDesc *sets, PairSource src, int use_pal, uint32_t seg_keys, uint32_t max_segs,
-                             uint32_t *counts, unsigned long long *work_counter, int n_sms, cudaStream_t s) {
+                             uint32_t *counts, unsigned long long *work_counter, int n_sms, int algo, cudaStream_t s) {
     if (src.count == 0) return cudaSuccess;
     cudaError_t e = cudaMemsetAsync(work_counter, 0, sizeof(unsigned long long), s);
     if (e != cudaSuccess) return e;
+    if (algo == 1) return launch_warp(sets, src, use_pal, seg_keys, max_segs, counts, work_counter, n_sms, s);
 #define X(i, C) \
     if (g_cfg == i) return launch_cfg<C>(sets, src, use_pal, seg_keys, max_segs, counts, work_counter, n_sms, s);
     GKD_FOR_EACH_CFG(X)
 #undef X
     return cudaErrorInvalidValue;
+}
+
+// ---- kernel 4, warp-cooperative variant ----------------------------------------------------------------
+// One warp owns a work item and streams both inputs through its own pair of 4 KiB rings (TMA bulk
+// copies of 128 keys, one mbarrier per slot).  A step loads 32 consecutive keys of each input with
+// coalesced, bank-conflict-free LDS.64 (one key per lane), takes x = min(a[31], b[31]), consumes every
+// key <= x of both windows (__ballot_sync + __popc give the two advances), and counts matches by a
+// 5-round shuffle binary search of each lane's A key in the B window.  No per-thread partition search,
+// no random shared-memory access, no CTA barrier in the streaming loop.
+constexpr int WK_BLK = GKD_WK_BLK;           // keys per TMA block (2 KiB: fewer, larger copies beat 4 x 1 KiB, the mbarrier traffic being the cost)
+#ifndef GKD_WK_NBLK
+#define GKD_WK_NBLK 2
+#endif
+constexpr int WK_NBLK = GKD_WK_NBLK;          // ring slots per input
+constexpr int WK_BATCH = WK_NBLK / 2;          // slots that must be free before more copies are requested
+constexpr int WK_CAP = WK_BLK * WK_NBLK;     // 512 keys = 4 KiB per input ring
+constexpr uint32_t WK_SMEM = WK_WARPS * (2 * WK_CAP * 8 + 2 * WK_NBLK * 8);
+
+struct WStream {
+    const uint64_t *keys;
+    uint32_t pos;     // next unconsumed key
+    uint32_t shift;   // ring index of position p is (p + shift) & (WK_CAP - 1)
+    uint32_t g0, v0;  // first block of the item and its warp-lifetime virtual block number
+    uint32_t issued, ready, limit;  // block numbers: next to request / first not known landed / one past last
+};
+
+__device__ __forceinline__ void wk_begin(WStream &s, const uint64_t *keys, uint32_t n, uint32_t pos0, uint32_t last_pos,
+                                         uint32_t vnext) {
+    s.keys = keys;
+    s.pos = pos0;
+    s.g0 = pos0 / WK_BLK;
+    s.v0 = vnext;
+    s.shift = (vnext - s.g0) * WK_BLK;
+    s.issued = s.g0;
+    s.ready = s.g0;
+    if (last_pos > n) last_pos = n;
+    s.limit = (last_pos + 32) / WK_BLK + 1;  // a step reads [pos, pos + 32)
+}
+
+__device__ __forceinline__ void wk_issue(WStream &s, uint32_t ring_addr, uint32_t bar_addr, uint32_t lane) {
+    uint32_t upto = s.pos / WK_BLK + WK_NBLK;
+    if (upto > s.limit) upto = s.limit;
+    if (upto > s.issued) {
+        __syncwarp();  // every lane is done reading the slots that are about to be overwritten
+        if (lane == 0) {
+            for (uint32_t g = s.issued; g < upto; g++) {
+                const uint32_t slot = (s.v0 + (g - s.g0)) & (WK_NBLK - 1);
+                mbar_expect_tx(bar_addr + slot * 8, WK_BLK * 8);
+                tma_load_1d(ring_addr + slot * (WK_BLK * 8), s.keys + (size_t)g * WK_BLK, WK_BLK * 8, bar_addr + slot * 8);
+            }
+        }
+        s.issued = upto;
+    }
+}
+
+__device__ __forceinline__ void wk_wait(WStream &s, uint32_t upto, uint32_t bar_addr) {
+    while (s.ready < upto) {
+        const uint32_t v = s.v0 + (s.ready - s.g0);
+        mbar_wait(bar_addr + (v & (WK_NBLK - 1)) * 8, (v / WK_NBLK) & 1u);
+        s.ready++;
+    }
+}
+
+// advance `ready` over blocks that have already landed, without blocking; every lane must have seen
+// the phase complete (that observation is what makes the copied bytes visible to it)
+__device__ __forceinline__ void wk_poll(WStream &s, uint32_t bar_addr) {
+    while (s.ready < s.issued) {
+        const uint32_t v = s.v0 + (s.ready - s.g0);
+        const bool ok = mbar_test(bar_addr + (v & (WK_NBLK - 1)) * 8, (v / WK_NBLK) & 1u);
+        if (!__all_sync(0xffffffffu, ok)) break;
+        s.ready++;
+    }
+}
+
+__global__ void __launch_bounds__(WK_WARPS * 32, WK_CTAS)
+    k_intersect_warp(const SetDesc *__restrict__ sets, PairSource src, int use_pal, uint32_t seg_keys, uint32_t max_segs,
+                     uint32_t *__restrict__ counts, unsigned long long *__restrict__ work_counter) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t base = smem_u32(smem_raw) + warp * (2 * WK_CAP * 8);
+    const uint32_t ringA = base, ringB = base + WK_CAP * 8;
+    const uint32_t barA = smem_u32(smem_raw) + WK_WARPS * (2 * WK_CAP * 8) + warp * (2 * WK_NBLK * 8);
+    const uint32_t barB = barA + WK_NBLK * 8;
+    if (lane == 0) {
+        for (int i = 0; i < WK_NBLK; i++) {
+            mbar_init(barA + i * 8, 1);
+            mbar_init(barB + i * 8, 1);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    const uint64_t total_items = src.count * (uint64_t)max_segs;
+    uint32_t vnextA = 0, vnextB = 0;
+    for (;;) {
+        unsigned long long item = 0;
+        uint32_t ida = 0, idb = 0;
+        if (lane == 0) {
+            item = atomicAdd(work_counter, 1ull);
+            if (item < total_items) decode_pair(src, item / max_segs, ida, idb);
+        }
+        item = __shfl_sync(0xffffffffu, item, 0);
+        if (item >= total_items) break;
+        ida = __shfl_sync(0xffffffffu, ida, 0);
+        idb = __shfl_sync(0xffffffffu, idb, 0);
+        const uint64_t pair = item / max_segs;
+        const uint32_t seg = (uint32_t)(item % max_segs);
+        const SetDesc SA = sets[ida], SB = sets[idb];
+        const uint64_t *keysA = use_pal ? SA.pal_keys : SA.keys;
+        const uint64_t *keysB = use_pal ? SB.pal_keys : SB.keys;
+        const uint32_t nA = use_pal ? SA.n_pal : SA.n;
+        const uint32_t nB = use_pal ? SB.n_pal : SB.n;
+        const uint64_t L = (uint64_t)nA + nB;
+        const uint64_t d0 = (uint64_t)seg * seg_keys;
+        if (nA == 0 || nB == 0 || d0 >= L) continue;
+        uint64_t d1 = d0 + seg_keys;
+        if (d1 > L) d1 = L;
+        // segment = merge-path diagonals [d0, d1): A keys [i0, i1) are mine; B is read from j0 on
+        const uint32_t i0 = d0 ? diag_search_global(keysA, nA, keysB, nB, d0) : 0u;
+        const uint32_t j0 = (uint32_t)(d0 - i0);
+        const uint32_t i1 = d1 < L ? diag_search_global(keysA, nA, keysB, nB, d1) : nA;
+        const uint32_t j1 = (uint32_t)(d1 - i1);
+
+        WStream sa, sb;
+        wk_begin(sa, keysA, nA, i0, i1, vnextA);
+        wk_begin(sb, keysB, nB, j0, j1 + 1, vnextB);  // B[j1] may equal my last A key
+        uint32_t cnt = 0;
+        const uint32_t loadedEndB = sb.limit * WK_BLK;  // B keys at or past this position are never loaded
+        // steps whose 32-key windows lie inside [.., i1) and the loaded part of B take the interior path
+        const int edgeA = (int)i1 - 32, edgeB = (int)loadedEndB - 32;
+        uint32_t trigA = 0, trigB = 0;  // ring bookkeeping is due once pos reaches these positions
+        uint32_t offA = (sa.pos + sa.shift) & (WK_CAP - 1), offB = (sb.pos + sb.shift) & (WK_CAP - 1);
+        while (sa.pos < i1) {  // only my A keys can produce matches; leftover B keys need no visit
+            if (sa.pos >= trigA || sb.pos >= trigB) {
+                // a block boundary was crossed: request the blocks whose slots are free, make sure the
+                // window [pos, pos + 32) has landed, and compute the next positions at which to look again
+                wk_issue(sa, ringA, barA, lane);
+                wk_issue(sb, ringB, barB, lane);
+                uint32_t need = (sa.pos + 31) / WK_BLK + 1;
+                wk_wait(sa, need < sa.limit ? need : sa.limit, barA);
+                need = (sb.pos + 31) / WK_BLK + 1;
+                wk_wait(sb, need < sb.limit ? need : sb.limit, barB);
+                wk_poll(sa, barA);
+                wk_poll(sb, barB);
+                // look again when two slots are free (issue) or the landed data runs out (wait)
+                uint32_t ti = sa.issued < sa.limit ? (sa.issued + WK_BATCH - WK_NBLK) * WK_BLK : 0xFFFFFFFFu;
+                uint32_t tw = sa.ready < sa.limit ? sa.ready * WK_BLK - 31 : 0xFFFFFFFFu;
+                trigA = ti < tw ? ti : tw;
+                ti = sb.issued < sb.limit ? (sb.issued + WK_BATCH - WK_NBLK) * WK_BLK : 0xFFFFFFFFu;
+                tw = sb.ready < sb.limit ? sb.ready * WK_BLK - 31 : 0xFFFFFFFFu;
+                trigB = ti < tw ? ti : tw;
+            }
+            const uint32_t pa = sa.pos + lane, pb = sb.pos + lane;
+            const uint32_t adrA = ringA + ((offA + lane) & (WK_CAP - 1)) * 8u;
+            const uint32_t adrB = ringB + ((offB + lane) & (WK_CAP - 1)) * 8u;
+            uint32_t nAc, nBc;
+            if ((int)sa.pos <= edgeA && (int)sb.pos <= edgeB) {
+                // interior step: every lane holds a loaded key of each input
+                const uint64_t a = lds64(adrA);
+                const uint64_t b = lds64(adrB);
+                const uint32_t ah = (uint32_t)(a >> 32), al = (uint32_t)a, bh = (uint32_t)(b >> 32), bl = (uint32_t)b;
+                const uint32_t href = __shfl_sync(0xffffffffu, ah, 0);
+                if (__all_sync(0xffffffffu, ah == href && bh == href)) {
+                    // all 64 keys share their high word (true for ~99 % of the windows of 42-bit keys):
+                    // the whole step runs on the low words
+                    const uint32_t amax = __shfl_sync(0xffffffffu, al, 31), bmax = __shfl_sync(0xffffffffu, bl, 31);
+                    const uint32_t x = amax < bmax ? amax : bmax;
+                    const bool ca = al <= x;
+                    nAc = __popc(__ballot_sync(0xffffffffu, ca));
+                    nBc = __popc(__ballot_sync(0xffffffffu, bl <= x));
+                    // lower bound of al among the 32 sorted low words of B: 4-ary, 4-ary, binary
+                    // (7 shuffles in 3 dependent levels instead of 5 dependent ones)
+                    const uint32_t q1 = __shfl_sync(0xffffffffu, bl, 7), q2 = __shfl_sync(0xffffffffu, bl, 15),
+                                   q3 = __shfl_sync(0xffffffffu, bl, 23);
+                    uint32_t lo = ((q1 < al) + (q2 < al) + (q3 < al)) * 8u;
+                    const uint32_t r1 = __shfl_sync(0xffffffffu, bl, lo + 1), r2 = __shfl_sync(0xffffffffu, bl, lo + 3),
+                                   r3 = __shfl_sync(0xffffffffu, bl, lo + 5);
+                    lo += ((r1 < al) + (r2 < al) + (r3 < al)) * 2u;
+                    const uint32_t t0 = __shfl_sync(0xffffffffu, bl, lo);
+                    const uint32_t t1 = __shfl_sync(0xffffffffu, bl, lo + 1 > 31u ? 31u : lo + 1);
+                    // the key equals B[lo] or, if B[lo] is smaller, B[lo+1]
+                    cnt += __popc(__ballot_sync(0xffffffffu, ca && (t0 == al || t1 == al)));
+                } else {
+                    const uint64_t amax = __shfl_sync(0xffffffffu, a, 31), bmax = __shfl_sync(0xffffffffu, b, 31);
+                    const uint64_t x = amax < bmax ? amax : bmax;
+                    const bool ca = a <= x;
+                    nAc = __popc(__ballot_sync(0xffffffffu, ca));
+                    nBc = __popc(__ballot_sync(0xffffffffu, b <= x));
+                    uint32_t lo = 0;
+#pragma unroll
+                    for (int st = 16; st >= 1; st >>= 1) {
+                        const uint64_t bv = __shfl_sync(0xffffffffu, b, lo + st - 1);
+                        if (bv < a) lo += st;
+                    }
+                    const uint64_t bm = __shfl_sync(0xffffffffu, b, lo);
+                    cnt += __popc(__ballot_sync(0xffffffffu, ca && bm == a));
+                }
+            } else {
+                // edge step: keys past my A range or past the loaded B blocks read as sentinels
+                const bool va = pa < i1;
+                const bool vb = pb < loadedEndB;
+                uint64_t a = KEY_SENTINEL, b = KEY_SENTINEL;
+                if (va) a = lds64(adrA);
+                if (vb) b = lds64(adrB);
+                const uint64_t amax = __shfl_sync(0xffffffffu, a, 31), bmax = __shfl_sync(0xffffffffu, b, 31);
+                const uint64_t x = amax < bmax ? amax : bmax;
+                const bool ca = va && a <= x;
+                nAc = __popc(__ballot_sync(0xffffffffu, ca));
+                nBc = __popc(__ballot_sync(0xffffffffu, b <= x));
+                uint32_t lo = 0;
+#pragma unroll
+                for (int st = 16; st >= 1; st >>= 1) {
+                    const uint64_t bv = __shfl_sync(0xffffffffu, b, lo + st - 1);
+                    if (bv < a) lo += st;
+                }
+                const uint64_t bm = __shfl_sync(0xffffffffu, b, lo);
+                cnt += __popc(__ballot_sync(0xffffffffu, ca && bm == a));
+            }
+            sa.pos += nAc;
+            sb.pos += nBc;
+            offA = (offA + nAc) & (WK_CAP - 1);
+            offB = (offB + nBc) & (WK_CAP - 1);
+        }
+        // drain copies that were requested but never needed, so the slots can be re-armed
+        wk_wait(sa, sa.issued, barA);
+        wk_wait(sb, sb.issued, barB);
+        vnextA += sa.issued - sa.g0;
+        vnextB += sb.issued - sb.g0;
+        if (lane == 0 && cnt) atomicAdd(&counts[pair], cnt);
+    }
+}
+
+static cudaError_t launch_warp(const SetDesc *sets, PairSource src, int use_pal, uint32_t seg_keys, uint32_t max_segs,
+                               uint32_t *counts, unsigned long long *work_counter, int n_sms, cudaStream_t s) {
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(k_intersect_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WK_SMEM);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    uint64_t items = src.count * (uint64_t)max_segs;
+    uint64_t grid = (uint64_t)n_sms * WK_CTAS;
+    uint64_t need = (items + WK_WARPS - 1) / WK_WARPS;
+    if (grid > need) grid = need;
+    k_intersect_warp<<<(unsigned)grid, WK_WARPS * 32, WK_SMEM, s>>>(sets, src, use_pal, seg_keys, max_segs, counts, work_counter);
+    return cudaGetLastError();
 }
 
 // ---- kernel 4, small-set variant ---------------------------------------------------------------------

@@ -423,3 +423,28 @@ def test_fuzz_against_oracle(orc):
                 inter, dist = orc.py_distance(psets[i], psets[j])
                 assert (int(gi[t]), gd[t]) == (inter, dist), (trial, k, letters, i, j)
                 t += 1
+
+
+@pytest.mark.parametrize("algo", ["cta", "warp"])
+def test_both_streaming_kernels_are_exact(orc, algo, monkeypatch):
+    """GKD_ISECT_ALGO pins the streaming kernel (auto picks by size balance): the CTA merge-path kernel
+    and the warp-cooperative ballot kernel must both be exact on balanced AND skewed pairs, whole and
+    segmented (the env var is read when a context is created)."""
+    monkeypatch.setenv("GKD_ISECT_ALGO", algo)
+    lens = [600_000, 610_000, 590_000, 30_000, 1_400_000, 25]
+    seqs = []
+    for g, n in enumerate(lens):
+        a = np.empty(n, dtype=np.uint8)
+        gkd.synth(a, 123, g % 2, g // 2, 0.03 if g // 2 else 0.0)
+        seqs.append(a.tobytes())
+    for k in (21, 16):
+        osets = [orc.IntSet(s, k) for s in seqs]
+        want_i = [osets[i].similarity(osets[j]) for i in range(len(seqs)) for j in range(i + 1, len(seqs))]
+        want_d = [osets[i].distance(osets[j]) for i in range(len(seqs)) for j in range(i + 1, len(seqs))]
+        for seg in (0, 3000, 100_000):
+            with gkd.Engine(k=k, segment_keys=seg) as e:
+                for s in seqs:
+                    e.add(s)
+                e.build()
+                gi, gd = e.all_vs_all()
+            assert gi.tolist() == want_i and gd.tolist() == want_d, (algo, k, seg)
