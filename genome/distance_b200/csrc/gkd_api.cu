@@ -514,7 +514,7 @@ int run_pairs(gkd_ctx *c, const HostPairs &hp, uint64_t *inter, double *dist) {
     uint64_t max_pal = 0;
     if (need_pal)
         for (auto &g : c->genomes) max_pal = std::max<uint64_t>(max_pal, g.desc.n_pal);
-    const int algo = intersect_select(min_n == UINT64_MAX ? 0 : min_n, max_n);
+    const int algo = intersect_select(min_n == UINT64_MAX ? 0 : min_n, max_n, nuc ? 2 * c->k : 8 * c->k);
     const bool small_main = c->cfg.segment_keys == 0 && max_n <= intersect_small_max_keys();
     const bool small_pal = max_pal <= intersect_small_max_keys();
 

@@ -115,7 +115,7 @@ cudaError_t launch_intersect(const SetDesc *sets, PairSource src, int use_pal, u
 cudaError_t launch_intersect_small(const SetDesc *sets, PairSource src, int use_pal, uint32_t *counts, int n_sms,
                                    cudaStream_t s);
 uint32_t intersect_small_max_keys();  // sets up to this size take the warp-per-pair kernel
-int intersect_select(uint64_t min_keys, uint64_t max_keys);  // streaming kernel for this workload: 0 = CTA merge path, 1 = warp-cooperative
+int intersect_select(uint64_t min_keys, uint64_t max_keys, int key_bits);  // streaming kernel for this workload: 0 = CTA merge path, 1 = warp-cooperative
 int intersect_min_segment();
 int intersect_items_per_sm(int algo);  // work items per SM that keep that kernel's workers busy  // smallest useful merge-path segment (one full round of the active config)
 cudaError_t launch_epilogue(const SetDesc *sets, PairSource src, const uint32_t *counts, const uint32_t *pal_counts,

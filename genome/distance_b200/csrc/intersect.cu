@@ -420,11 +420,15 @@ cudaError_t intersect_configure() {
 // The warp-cooperative kernel advances both inputs by the keys below min(a[31], b[31]) per step, which
 // is efficient when the two sets have similar key density; a pair of very different sizes makes it
 // crawl through the denser set 32 keys at a time, where the CTA kernel's merge-path rounds stay
-// balanced.  Auto mode therefore takes the warp kernel only when the participating sets are within
-// a factor of four in size.
-int intersect_select(uint64_t min_keys, uint64_t max_keys) {
+// balanced.  Its fast path also needs the 64 window keys to share their high 32 bits, i.e. sets that
+// are dense relative to the key space above bit 32 (42-bit DNA keys of Mbp genomes: yes; 64-bit
+// protein keys: no).  Auto mode takes the warp kernel only when both hold; otherwise the CTA kernel.
+int intersect_select(uint64_t min_keys, uint64_t max_keys, int key_bits) {
     if (g_algo_mode != 2) return g_algo_mode;
-    return (min_keys > 0 && max_keys <= 4 * min_keys) ? 1 : 0;
+    if (min_keys == 0 || max_keys > 4 * min_keys) return 0;
+    const int hi_bits = key_bits > 32 ? key_bits - 32 : 0;
+    if (hi_bits >= 40 || (min_keys >> hi_bits) < 1024) return 0;  // fewer than ~1000 keys per high-word value
+    return 1;
 }
 
 int intersect_items_per_sm(int algo) { return algo ? WK_CTAS * WK_WARPS * 6 : 3 * 8; }
