@@ -595,7 +595,9 @@ __global__ void __launch_bounds__(WK_WARPS * 32, WK_CTAS)
         // steps whose 32-key windows lie inside [.., i1) and the loaded part of B take the interior path
         const int edgeA = (int)i1 - 32, edgeB = (int)loadedEndB - 32;
         uint32_t trigA = 0, trigB = 0;  // ring bookkeeping is due once pos reaches these positions
-        uint32_t offA = (sa.pos + sa.shift) & (WK_CAP - 1), offB = (sb.pos + sb.shift) & (WK_CAP - 1);
+        // per-lane byte offset of this lane's key inside each ring, advanced by the consumed counts
+        constexpr uint32_t RING_MASK = (WK_CAP - 1) * 8u;
+        uint32_t laneA = ((sa.pos + sa.shift + lane) * 8u) & RING_MASK, laneB = ((sb.pos + sb.shift + lane) * 8u) & RING_MASK;
         while (sa.pos < i1) {  // only my A keys can produce matches; leftover B keys need no visit
             if (sa.pos >= trigA || sb.pos >= trigB) {
                 // a block boundary was crossed: request the blocks whose slots are free, make sure the
@@ -617,8 +619,8 @@ __global__ void __launch_bounds__(WK_WARPS * 32, WK_CTAS)
                 trigB = ti < tw ? ti : tw;
             }
             const uint32_t pa = sa.pos + lane, pb = sb.pos + lane;
-            const uint32_t adrA = ringA + ((offA + lane) & (WK_CAP - 1)) * 8u;
-            const uint32_t adrB = ringB + ((offB + lane) & (WK_CAP - 1)) * 8u;
+            const uint32_t adrA = ringA + laneA;
+            const uint32_t adrB = ringB + laneB;
             uint32_t nAc, nBc;
             if ((int)sa.pos <= edgeA && (int)sb.pos <= edgeB) {
                 // interior step: every lane holds a loaded key of each input
@@ -638,10 +640,10 @@ __global__ void __launch_bounds__(WK_WARPS * 32, WK_CTAS)
                     // (7 shuffles in 3 dependent levels instead of 5 dependent ones)
                     const uint32_t q1 = __shfl_sync(0xffffffffu, bl, 7), q2 = __shfl_sync(0xffffffffu, bl, 15),
                                    q3 = __shfl_sync(0xffffffffu, bl, 23);
-                    uint32_t lo = ((q1 < al) + (q2 < al) + (q3 < al)) * 8u;
+                    uint32_t lo = q3 < al ? 24u : (q2 < al ? 16u : (q1 < al ? 8u : 0u));  // probes are sorted
                     const uint32_t r1 = __shfl_sync(0xffffffffu, bl, lo + 1), r2 = __shfl_sync(0xffffffffu, bl, lo + 3),
                                    r3 = __shfl_sync(0xffffffffu, bl, lo + 5);
-                    lo += ((r1 < al) + (r2 < al) + (r3 < al)) * 2u;
+                    lo += r3 < al ? 6u : (r2 < al ? 4u : (r1 < al ? 2u : 0u));
                     const uint32_t t0 = __shfl_sync(0xffffffffu, bl, lo);
                     const uint32_t t1 = __shfl_sync(0xffffffffu, bl, lo + 1 > 31u ? 31u : lo + 1);
                     // the key equals B[lo] or, if B[lo] is smaller, B[lo+1]
@@ -684,8 +686,8 @@ __global__ void __launch_bounds__(WK_WARPS * 32, WK_CTAS)
             }
             sa.pos += nAc;
             sb.pos += nBc;
-            offA = (offA + nAc) & (WK_CAP - 1);
-            offB = (offB + nBc) & (WK_CAP - 1);
+            laneA = (laneA + nAc * 8u) & RING_MASK;
+            laneB = (laneB + nBc * 8u) & RING_MASK;
         }
         // drain copies that were requested but never needed, so the slots can be re-armed
         wk_wait(sa, sa.issued, barA);
