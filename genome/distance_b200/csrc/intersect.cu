@@ -528,6 +528,19 @@ __device__ __forceinline__ void wk_wait(WStream &s, uint32_t upto, uint32_t bar_
     }
 }
 
+__device__ __forceinline__ void wk_poll(WStream &s, uint32_t bar_addr);
+
+// one bookkeeping visit for a stream; returns the position at which the next visit is due
+__device__ __forceinline__ uint32_t wk_service(WStream &s, uint32_t ring_addr, uint32_t bar_addr, uint32_t lane) {
+    wk_issue(s, ring_addr, bar_addr, lane);
+    const uint32_t need = (s.pos + 31) / WK_BLK + 1;
+    wk_wait(s, need < s.limit ? need : s.limit, bar_addr);
+    if (WK_NBLK > 2) wk_poll(s, bar_addr);
+    const uint32_t ti = s.issued < s.limit ? (s.issued + WK_BATCH - WK_NBLK) * WK_BLK : 0xFFFFFFFFu;
+    const uint32_t tw = s.ready < s.limit ? s.ready * WK_BLK - 31 : 0xFFFFFFFFu;
+    return ti < tw ? ti : tw;
+}
+
 // advance `ready` over blocks that have already landed, without blocking; every lane must have seen
 // the phase complete (that observation is what makes the copied bytes visible to it)
 __device__ __forceinline__ void wk_poll(WStream &s, uint32_t bar_addr) {
@@ -599,25 +612,11 @@ __global__ void __launch_bounds__(WK_WARPS * 32, WK_CTAS)
         constexpr uint32_t RING_MASK = (WK_CAP - 1) * 8u;
         uint32_t laneA = ((sa.pos + sa.shift + lane) * 8u) & RING_MASK, laneB = ((sb.pos + sb.shift + lane) * 8u) & RING_MASK;
         while (sa.pos < i1) {  // only my A keys can produce matches; leftover B keys need no visit
-            if (sa.pos >= trigA || sb.pos >= trigB) {
-                // a block boundary was crossed: request the blocks whose slots are free, make sure the
-                // window [pos, pos + 32) has landed, and compute the next positions at which to look again
-                wk_issue(sa, ringA, barA, lane);
-                wk_issue(sb, ringB, barB, lane);
-                uint32_t need = (sa.pos + 31) / WK_BLK + 1;
-                wk_wait(sa, need < sa.limit ? need : sa.limit, barA);
-                need = (sb.pos + 31) / WK_BLK + 1;
-                wk_wait(sb, need < sb.limit ? need : sb.limit, barB);
-                wk_poll(sa, barA);
-                wk_poll(sb, barB);
-                // look again when two slots are free (issue) or the landed data runs out (wait)
-                uint32_t ti = sa.issued < sa.limit ? (sa.issued + WK_BATCH - WK_NBLK) * WK_BLK : 0xFFFFFFFFu;
-                uint32_t tw = sa.ready < sa.limit ? sa.ready * WK_BLK - 31 : 0xFFFFFFFFu;
-                trigA = ti < tw ? ti : tw;
-                ti = sb.issued < sb.limit ? (sb.issued + WK_BATCH - WK_NBLK) * WK_BLK : 0xFFFFFFFFu;
-                tw = sb.ready < sb.limit ? sb.ready * WK_BLK - 31 : 0xFFFFFFFFu;
-                trigB = ti < tw ? ti : tw;
-            }
+            // ring bookkeeping only when a stream reaches its next trigger position: request the blocks
+            // whose slots are free, make sure the window [pos, pos + 32) has landed, and compute the next
+            // position at which to look again (a slot frees up, or the landed data runs out)
+            if (sa.pos >= trigA) trigA = wk_service(sa, ringA, barA, lane);
+            if (sb.pos >= trigB) trigB = wk_service(sb, ringB, barB, lane);
             const uint32_t pa = sa.pos + lane, pb = sb.pos + lane;
             const uint32_t adrA = ringA + laneA;
             const uint32_t adrB = ringB + laneB;
