@@ -526,11 +526,12 @@ int run_pairs(gkd_ctx *c, const HostPairs &hp, uint64_t *inter, double *dist) {
         if (hp.count >= target_items) seg = max_l;
         else {
             uint64_t total_keys = (uint64_t)(sum_bytes / 8.0L);
-            seg = std::max<uint64_t>(total_keys / target_items, 16384);
+            // a segment must amortise its two global diagonal searches: ~5 CTA rounds, or ~70 warp steps
+            seg = std::max<uint64_t>(total_keys / target_items, algo ? 4096 : 16384);
             seg = std::min<uint64_t>(seg, max_l);
         }
     }
-    seg = std::max<uint64_t>(seg, (uint64_t)intersect_min_segment());
+    seg = std::max<uint64_t>(seg, (uint64_t)intersect_min_segment(algo));
     seg = std::min<uint64_t>(seg, 0xFFFF0000ull);
     const uint32_t max_segs = (uint32_t)((max_l + seg - 1) / seg);
 

@@ -116,8 +116,8 @@ cudaError_t launch_intersect_small(const SetDesc *sets, PairSource src, int use_
                                    cudaStream_t s);
 uint32_t intersect_small_max_keys();  // sets up to this size take the warp-per-pair kernel
 int intersect_select(uint64_t min_keys, uint64_t max_keys, int key_bits);  // streaming kernel for this workload: 0 = CTA merge path, 1 = warp-cooperative
-int intersect_min_segment();
-int intersect_items_per_sm(int algo);  // work items per SM that keep that kernel's workers busy  // smallest useful merge-path segment (one full round of the active config)
+int intersect_min_segment(int algo);   // smallest useful merge-path segment of that kernel
+int intersect_items_per_sm(int algo);  // work items per SM that keep that kernel's workers busy
 cudaError_t launch_epilogue(const SetDesc *sets, PairSource src, const uint32_t *counts, const uint32_t *pal_counts,
                             int both_strands, uint64_t *inter, double *dist, cudaStream_t s);
 // synthetic data

@@ -433,7 +433,8 @@ int intersect_select(uint64_t min_keys, uint64_t max_keys, int key_bits) {
 
 int intersect_items_per_sm(int algo) { return algo ? WK_CTAS * WK_WARPS * 6 : 3 * 8; }
 
-int intersect_min_segment() {
+int intersect_min_segment(int algo) {
+    if (algo == 1) return 1024;
 #define X(i, C) \
     if (g_cfg == i) return C::W;
     GKD_FOR_EACH_CFG(X)
