@@ -4,7 +4,8 @@
 //   fastaDist  -> FastaDistanceProcessor.java  (options :66-90, validation :93-112, report :134-194)
 //   genomes    -> GenomeProcessor.java         (options :54-79, validation :82-116, report :119-150)
 //   fastaReps  -> FastaDistanceRepsProcessor.java (options :52-76, validation :78-91, report :110-147);
-//                 a caller of the same distance(), SURVEY section 8f "next" row 1
+//   distReps   -> DistanceRepsProcessor.java (options :66-83, validation :154-177, run :180-275);
+//                 callers of the same distance(), SURVEY section 8f "next" row 1
 //
 // Dispatch mirrors App.java:35-111 (args[0] selects the processor).  Reports go to stdout or -o,
 // log lines to stderr (logback.xml:4-13).  Every distance comes from libgkd.so; there is no CPU path.
@@ -491,11 +492,140 @@ int genomes(const std::vector<std::string> &args) {
     return 0;
 }
 
+// ---- distReps ------------------------------------------------------------------------------------
+const std::vector<OptSpec> DISTREPS_OPTS = {
+    {{"--kmerSize", "-K", "--kmer"}, true, "kmer size to use for distance computation"},
+    {{"--sourceType", "--type", "-t"}, true, "type of genome sources (DIR = directory of GTO files; FASTA = directory of FASTA files)"},
+    {{"--dist"}, true, "maximum distance for a representative neighborhood"},
+    {{"--outDir", "-D"}, true, "output directory name"},
+    {{"--clear"}, false, "erase the output directory before processing"},
+    {{"--device"}, true, "CUDA device ordinal (additive option; default 0)"},
+    {{"--help", "-h"}, false, "display command-line usage"},
+    {{"--verbose", "-v"}, false, "display more frequent log messages"},
+};
+
+// DistanceRepsProcessor.java: pass 1 picks representatives greedily (:185-201), pass 2 assigns every
+// genome to its closest representative (:220-262) and writes rep%.4f_K%d.list.tbl / .stats.tbl (:212-274)
+int distReps(const std::vector<std::string> &args) {
+    Parsed p = parseOptions(DISTREPS_OPTS, args);
+    if (p.values.count("--help")) {
+        printUsage("distReps", DISTREPS_OPTS, "inDir1 inDir2 ...");
+        return 0;
+    }
+    // setMultiReportDefaults (:146-151)
+    int kmerSize = p.values.count("--kmerSize") ? toInt("--kmerSize", p.values["--kmerSize"]) : 9;
+    double maxDist = p.values.count("--dist") ? toDouble("--dist", p.values["--dist"]) : 0.97;
+    std::string sourceType = p.values.count("--sourceType") ? p.values["--sourceType"] : "DIR";
+    std::string outDir = p.values.count("--outDir") ? p.values["--outDir"] : "repDb";
+    int device = p.values.count("--device") ? toInt("--device", p.values["--device"]) : 0;
+    if (sourceType != "DIR" && sourceType != "FASTA")
+        throw ParseFailureException("\"" + sourceType + "\" is not a valid value for \"--sourceType\"");
+    if (p.positional.empty()) throw ParseFailureException("Argument \"inDir1 inDir2 ...\" is required");
+    // validateMultiReportParms (:154-177)
+    if (kmerSize < 4) throw ParseFailureException("Kmer size must be at least 4.");
+    if (maxDist <= 0.0 || maxDist >= 1.0) throw ParseFailureException("Distance must be strictly between 0 and 1.");
+    for (auto &d : p.positional)
+        if (!exists(d)) throw IOException("Genome source " + d + " is not found.");
+    if (!isDir(outDir) && mkdir(outDir.c_str(), 0777) != 0) throw IOException("Cannot create output directory " + outDir + ".");
+
+    KmerEngine engine(KmerType::DNA, kmerSize, device);
+    std::vector<SequenceKmers> all;
+    for (auto &d : p.positional) {
+        std::vector<GenomeData> src = loadSource(sourceType, d);
+        logInfo(std::to_string(src.size()) + " genomes found in " + d + ".");
+        for (auto &g : src) all.push_back(engine.genomeKmers(g.contigs, g.id, g.name));
+    }
+    logInfo(std::to_string(all.size()) + " total genomes found in all sources.");
+    engine.build();
+    // pass 1: a genome joins the representative set unless a current representative is within maxDist
+    logInfo("Starting first pass to find representatives.");
+    std::vector<size_t> reps;            // indices into `all`, in insertion order
+    std::vector<char> isRep(all.size(), 0);
+    std::vector<uint32_t> a, b;
+    std::vector<double> dist;
+    for (size_t i = 0; i < all.size(); i++) {
+        bool belongs = false;
+        if (!reps.empty()) {
+            a.clear();
+            b.clear();
+            for (size_t r : reps) {
+                a.push_back(all[r].handle());  // x.distance(kmers) (:190)
+                b.push_back(all[i].handle());
+            }
+            dist.assign(a.size(), 1.0);
+            engine.check(gkd_pairs(engine.raw(), a.data(), b.data(), a.size(), nullptr, dist.data()));
+            for (double d : dist)
+                if (d <= maxDist) belongs = true;
+        }
+        if (!belongs) {
+            reps.push_back(i);
+            isRep[i] = 1;
+        }
+    }
+    logInfo(std::to_string(reps.size()) + " total representatives found for " + std::to_string(all.size()) + " genomes.");
+    // pass 2: closest representative of every other genome in one batched call; ties keep the
+    // representative met first (Result.merge keeps the left operand, :120-122; the reference walks its
+    // HashMap, whose order is unspecified, so insertion order is used here)
+    std::vector<uint32_t> q, r;
+    std::vector<size_t> qIdx;
+    for (size_t i = 0; i < all.size(); i++)
+        if (!isRep[i]) {
+            q.push_back(all[i].handle());
+            qIdx.push_back(i);
+        }
+    for (size_t x : reps) r.push_back(all[x].handle());
+    std::vector<double> block;
+    if (!q.empty()) engine.queryVsRef(q, r, block);
+    std::vector<size_t> bestRep(all.size());
+    std::vector<double> bestDist(all.size(), 0.0);
+    for (size_t i = 0; i < all.size(); i++) bestRep[i] = i;
+    for (size_t qi = 0; qi < qIdx.size(); qi++) {
+        // reduce(NULL_RESULT, merge): start from distance 1.0 and replace only on a strictly smaller distance
+        double best = 1.0;
+        size_t arg = reps[0];  // only kept if no distance is below 1.0, which pass 1 rules out
+        for (size_t ri = 0; ri < reps.size(); ri++) {
+            const double d = block[qi * reps.size() + ri];
+            if (d < best) {
+                best = d;
+                arg = reps[ri];
+            }
+        }
+        bestRep[qIdx[qi]] = arg;
+        bestDist[qIdx[qi]] = best;
+    }
+    char prefix[64];
+    snprintf(prefix, sizeof(prefix), "rep%.4f_K%d", maxDist, kmerSize);
+    std::map<std::string, long> neighborCounts;
+    {
+        std::ofstream list(outDir + "/" + prefix + ".list.tbl");
+        if (!list) throw IOException("Cannot write to " + outDir + ".");
+        list << "genome_id\tgenome_name\trep_id\trep_name\tdistance\n";
+        for (size_t i = 0; i < all.size(); i++) {
+            const SequenceKmers &rep = all[bestRep[i]];
+            list << all[i].getGenomeId() << '\t' << all[i].getGenomeName() << '\t' << rep.getGenomeId() << '\t'
+                 << rep.getGenomeName() << '\t' << javaDouble(bestDist[i]) << '\n';
+            neighborCounts[rep.getGenomeId()]++;
+        }
+    }
+    logInfo(std::to_string(all.size()) + " total genomes placed.");
+    {
+        // CountMap.sortedCounts(): largest neighbourhood first (ties by id)
+        std::vector<std::pair<std::string, long>> counts(neighborCounts.begin(), neighborCounts.end());
+        std::stable_sort(counts.begin(), counts.end(), [](const auto &x, const auto &y) { return x.second > y.second; });
+        std::map<std::string, std::string> names;
+        for (size_t x : reps) names[all[x].getGenomeId()] = all[x].getGenomeName();
+        std::ofstream stats(outDir + "/" + prefix + ".stats.tbl");
+        stats << "rep_id\trep_name\tsize\n";
+        for (auto &c : counts) stats << c.first << '\t' << names[c.first] << '\t' << c.second << '\n';
+    }
+    return 0;
+}
+
 }  // namespace
 
 int main(int argc, char **argv) {
     if (argc < 2) {
-        fprintf(stderr, "usage: gkd <fastaDist|genomes|fastaReps> [options]\n");
+        fprintf(stderr, "usage: gkd <fastaDist|genomes|fastaReps|distReps> [options]\n");
         return 2;
     }
     std::string command = argv[1];
@@ -504,13 +634,16 @@ int main(int argc, char **argv) {
         if (command == "fastaDist") return fastaDist(rest);
         if (command == "genomes") return genomes(rest);
         if (command == "fastaReps") return fastaReps(rest);
+        if (command == "distReps") return distReps(rest);
         // App.java:104 -- IllegalArgumentException("Invalid command " + command)
-        fprintf(stderr, "Invalid command %s. (gkd implements the k-mer distance hot path: fastaDist, genomes, fastaReps)\n", command.c_str());
+        fprintf(stderr, "Invalid command %s. (gkd implements the k-mer distance hot path: fastaDist, genomes, fastaReps, distReps)\n", command.c_str());
         return 2;
     } catch (const ParseFailureException &e) {
         fprintf(stderr, "%s\n", e.what());  // BaseProcessor prints the message and the usage
-        printUsage(command, command == "genomes" ? GENOME_OPTS : (command == "fastaReps" ? REPS_OPTS : FASTA_OPTS),
-                   command == "genomes" ? "gtoDir gtoDir1 gtoDir2 ..." : "");
+        printUsage(command,
+                   command == "genomes" ? GENOME_OPTS
+                                        : (command == "fastaReps" ? REPS_OPTS : (command == "distReps" ? DISTREPS_OPTS : FASTA_OPTS)),
+                   command == "genomes" ? "gtoDir gtoDir1 gtoDir2 ..." : (command == "distReps" ? "inDir1 inDir2 ..." : ""));
         return 1;
     } catch (const IOException &e) {
         fprintf(stderr, "%s\n", e.what());

@@ -150,3 +150,66 @@ def test_fastareps_matches_reference_greedy(orc, tmp_path):
         assert out.rstrip("\n").split("\n") == want, max_dist
         assert "%d representatives found for %d sequences." % (len(reps), len(recs)) in err
     assert len(want) > 4  # the tightest threshold splits the families
+
+
+def test_distreps_validation(tmp_path):
+    d = tmp_path / "g"
+    d.mkdir()
+    rc, out, err = run(["distReps", "-K", "3", str(d)])
+    assert rc == 1 and err.startswith("Kmer size must be at least 4.")
+    for bad in ("0", "1", "1.5"):
+        rc, out, err = run(["distReps", "--dist", bad, str(d)])
+        assert rc == 1 and err.startswith("Distance must be strictly between 0 and 1.")
+    rc, out, err = run(["distReps", str(tmp_path / "missing")])
+    assert rc == 1 and "Genome source %s is not found." % (tmp_path / "missing") in err
+    rc, out, err = run(["distReps"])
+    assert rc == 1 and "is required" in err
+
+
+@pytest.mark.gpu
+def test_distreps_matches_reference_greedy(orc, tmp_path):
+    """DistanceRepsProcessor.java:185-274: greedy representatives, closest-representative assignment,
+    list and stats files named rep%.4f_K%d.*"""
+    rng = random.Random(44)
+    bases = [[_rand(rng, 9000), _rand(rng, 4000)] for _ in range(3)]
+    genomes = {}
+    for i in range(11):
+        b = bases[i % 3]
+        genomes["%d.%d" % (100 + i % 3, i)] = [_mut(rng, c, 0.01 * (i // 3)) for c in b]
+    src = tmp_path / "gtos"
+    src.mkdir()
+    for gid, contigs in genomes.items():
+        with open(src / (gid + ".gto"), "w") as f:
+            json.dump({"id": gid, "scientific_name": "Genus species " + gid,
+                       "contigs": [{"id": "c%d" % j, "dna": c} for j, c in enumerate(contigs)]}, f)
+    order = sorted(genomes)  # the source lists genomes in file-name order
+    k, max_dist = 12, 0.6
+    sets = {g: orc.StrSet(genomes[g], k) for g in order}
+    reps = []
+    for g in order:
+        if not any(sets[r].distance(sets[g]) <= max_dist for r in reps):
+            reps.append(g)
+    want_list = ["genome_id\tgenome_name\trep_id\trep_name\tdistance"]
+    counts = {}
+    for g in order:
+        if g in reps:
+            rep, d = g, 0.0
+        else:
+            rep, d = None, 1.0
+            for r in reps:
+                x = sets[g].distance(sets[r])
+                if x < d:
+                    rep, d = r, x
+        counts[rep] = counts.get(rep, 0) + 1
+        want_list.append("\t".join([g, "Genus species " + g, rep, "Genus species " + rep, orc.java_double(d)]))
+    out_dir = tmp_path / "out"
+    rc, out, err = run(["distReps", "-K", str(k), "--dist", str(max_dist), "-D", str(out_dir), str(src)])
+    assert rc == 0, err
+    prefix = "rep%.4f_K%d" % (max_dist, k)
+    assert (out_dir / (prefix + ".list.tbl")).read_text().rstrip("\n").split("\n") == want_list
+    stats = (out_dir / (prefix + ".stats.tbl")).read_text().rstrip("\n").split("\n")
+    assert stats[0] == "rep_id\trep_name\tsize"
+    got = {ln.split("\t")[0]: int(ln.split("\t")[2]) for ln in stats[1:]}
+    assert got == counts and 1 < len(reps) < len(order)
+    sizes = [int(ln.split("\t")[2]) for ln in stats[1:]]
+    assert sizes == sorted(sizes, reverse=True)
