@@ -115,6 +115,11 @@ def test_genomes_report_matches_oracle_text(orc, tmp_path):
     assert rc == 0, err
     assert out.rstrip("\n").split("\n") == want  # deterministic order in this command
     assert "6 comparisons output." in err
+    # downstream contract (DistanceCheckProcessor.java:159-169, GroupTypeSpec.java:84,90): three
+    # tab-separated columns, column 3 parses as a Java double, unrelated genomes print exactly 1.0
+    rows = [ln.split("\t") for ln in out.rstrip("\n").split("\n")[1:]]
+    assert all(len(r) == 3 and 0.0 <= float(r[2]) <= 1.0 for r in rows)
+    assert any(r[2] == "1.0" for r in rows)
 
 
 def test_fastareps_validation():
