@@ -319,7 +319,8 @@ def main():
             traffic = tj["dram_bytes_per_algorithmic_byte"] * isect_bytes
         except Exception:
             traffic = None
-    roofline = {"kernel": "k_intersect", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+    kname = {0: "k_intersect<IsectCfg<192,17,9,3>> (CTA merge path)", 1: "k_intersect_warp", 2: "k_intersect_small"}
+    roofline = {"kernel": kname.get(int(mets[-1].get("intersect_kernel", 0)), "k_intersect"), "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": isect_bytes, "ms_per_launch": isect_ms,
                 "note": "achieved = 8*(|A|+|B|) bytes per pair / CUDA-event time; rows served from L2 can push it past HBM peak"}

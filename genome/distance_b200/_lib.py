@@ -22,7 +22,7 @@ class GkdMetrics(C.Structure):
     _fields_ = [("pack_ms", C.c_double), ("encode_ms", C.c_double), ("sort_ms", C.c_double), ("unique_ms", C.c_double),
                 ("intersect_ms", C.c_double), ("epilogue_ms", C.c_double), ("h2d_ms", C.c_double), ("d2h_ms", C.c_double),
                 ("residues_packed", C.c_uint64), ("kmer_positions", C.c_uint64), ("keys_sorted", C.c_uint64),
-                ("sort_passes", C.c_uint32), ("reserved0", C.c_uint32), ("keys_unique", C.c_uint64), ("pairs", C.c_uint64),
+                ("sort_passes", C.c_uint32), ("intersect_kernel", C.c_uint32), ("keys_unique", C.c_uint64), ("pairs", C.c_uint64),
                 ("intersect_bytes", C.c_uint64), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64),
                 ("launches", C.c_uint64), ("intersect_launches", C.c_uint64), ("reserved", C.c_uint64 * 6)]
 

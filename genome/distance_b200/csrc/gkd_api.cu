@@ -517,6 +517,7 @@ int run_pairs(gkd_ctx *c, const HostPairs &hp, uint64_t *inter, double *dist) {
     const int algo = intersect_select(min_n == UINT64_MAX ? 0 : min_n, max_n, nuc ? 2 * c->k : 8 * c->k);
     const bool small_main = c->cfg.segment_keys == 0 && max_n <= intersect_small_max_keys();
     const bool small_pal = max_pal <= intersect_small_max_keys();
+    c->m.intersect_kernel = small_main ? 2u : (uint32_t)algo;
 
     // merge-path segmenting: whole pairs when there are enough of them to fill the machine
     const uint64_t max_l = std::max<uint64_t>(2 * max_n, 1);
