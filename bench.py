@@ -4,19 +4,22 @@
 Workload (config.workload): BASELINE configs[1] -- N synthetic 5 Mbp genomes (10 families of mutated
 descendants, SURVEY 8d generator), DNA K=21, all-vs-all Jaccard distance = N(N-1)/2 pairs.  Default
 N=1000 (499,500 pairs) on one B200.  One "step" = one full pass of the hot path: kernel 1 (pack) ->
-2 (canonical encode) -> 3 (radix sort + unique) -> 4 (merge-path intersect) -> 5 (distance epilogue).
+2 (canonical encode + mix) -> 3 (radix sort + unique + bucket tables) -> 4 (bucket-merge intersect) ->
+5 (distance epilogue).
 
   value  : pairs/s with the genome text already resident in HBM when the step starts
   e2e    : pairs/s through the C ABI with HOST (pinned) text buffers in, host result arrays out
-  roofline: k_intersect algorithmic bytes 8*(|A|+|B|) per pair / CUDA-event time of the launch
+  roofline: kernel 4 algorithmic bytes 8*(|A|+|B|) per pair / CUDA-event time of its launches
   cpu_baseline: the oracle's HashSet<String> port of the reference on a bounded sample (rank 0, N=1)
 
 N>1 (torchrun): strong scaling of the same workload -- rank r builds the sets of its slice of the
-genomes, the set arenas are exchanged over NCCL (one broadcast per owner), every rank intersects its
-contiguous slice of the pair enumeration; no cross-rank reduction.
+genomes and owns a set of rank blocks of the pair matrix; the peers' sets arrive as panels over NCCL
+send/recv while earlier blocks are being intersected and are adopted in place
+(genome/distance_b200/sharding.py: ring_all_vs_all); no cross-rank reduction.
 
-`--impl reference` times the reference's own CPU algorithm (oracle string-set port; the Java
-original cannot run here: no JVM, arithmetic in an un-vendored artifact) on a bounded sample.
+`--impl reference` times the reference's own CPU algorithm (oracle string-set port of
+FastaDistanceProcessor; the Java original cannot run here: no JVM, arithmetic in an un-vendored artifact)
+on a bounded sample.  That arm never loads the product library.
 """
 from __future__ import annotations
 
@@ -48,9 +51,13 @@ def parse_args():
     ap.add_argument("--length", type=int, default=int(os.environ.get("GKD_BENCH_LENGTH", "5000000")))
     ap.add_argument("--families", type=int, default=10)
     ap.add_argument("--k", type=int, default=21)
-    ap.add_argument("--cpu-sample", type=int, default=int(os.environ.get("GKD_BENCH_CPU_SAMPLE", "8")))
+    ap.add_argument("--panel", type=int, default=int(os.environ.get("GKD_BENCH_PANEL", "64")),
+                    help="sets per exchanged panel (N>1)")
+    ap.add_argument("--cpu-sample", type=int, default=int(os.environ.get("GKD_BENCH_CPU_SAMPLE", "24")))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--other-configs", action="store_true", default=os.environ.get("GKD_BENCH_OTHER", "0") == "1",
+                    help="also run BASELINE configs 1, 3 and 5 at full size (N=1) and report them as other_configs")
     return ap.parse_args()
 
 
@@ -65,6 +72,17 @@ def genome_params(g: int, n_genomes: int, families: int):
 def workload_name(a):
     return (f"{a.genomes} synthetic {a.length / 1e6:g} Mbp genomes all-vs-all DNA k-mer Jaccard, K={a.k} "
             f"({a.genomes * (a.genomes - 1) // 2} pairs)")
+
+
+def config_dict(a, world):
+    """identical in both arms: the workload the metric is quoted on, and the bounded sample of it that the CPU
+    arm (reference arm / cpu_baseline) actually runs"""
+    n = a.genomes
+    return {"workload": workload_name(a), "k": a.k, "genomes": n, "genome_bp": a.length, "pairs": n * (n - 1) // 2,
+            "families": a.families,
+            "cpu_sample": f"CPU legs run the first {a.cpu_sample} genomes of this workload "
+                          f"({a.cpu_sample * (a.cpu_sample - 1) // 2} pairs) with the reference's batch=20 decomposition",
+            "l2": "inputs (21 MB per set, 21 GB total) are far larger than L2; no flush needed"}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -121,57 +139,86 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------
-# reference arm / cpu baseline (oracle port; the only place bench.py executes oracle/)
+# reference arm / cpu baseline (oracle port; the only place bench.py executes oracle/, and this leg never
+# imports the product package: inputs come from the oracle's own numpy port of the generator)
 # ------------------------------------------------------------------------------------------------
 def host_sample(a, n_sample: int):
-    import numpy as np
-
-    import genome.distance_b200 as gkd
+    from oracle import synth as osynth
 
     seqs = []
     for g in range(n_sample):
         fam, mem, rate = genome_params(g, a.genomes, a.families)
-        buf = np.empty(a.length, dtype=np.uint8)
-        gkd.synth(buf, SEED, fam, mem, rate)
-        seqs.append(buf.tobytes())
+        seqs.append(osynth.synth(a.length, SEED, fam, mem, rate).tobytes())
     return seqs
 
 
-def run_cpu_reference(a, n_sample: int):
-    """FastaDistanceProcessor's algorithm (HashSet<String> port, rows in parallel) on the first
-    n_sample genomes of the workload; returns (pairs/s, seconds, threads, pairs)."""
+def run_cpu_reference(a, n_sample: int, seqs=None, mode: int = 0):
+    """FastaDistanceProcessor's algorithm on the first n_sample genomes of the workload with the reference's
+    own decomposition: batches of 20 sets cached serially (:151-155), rows of a batch in parallel (:157-158),
+    the set of a column outside the batch rebuilt for every pair (:183-184).  mode 0 = HashSet<String> port
+    (the reference's representation), mode 1 = sorted canonical uint64 sets + merge (a stronger CPU line).
+    Returns (pairs/s, seconds, threads, pairs)."""
     from oracle import oracle as orc
 
-    seqs = host_sample(a, n_sample)
+    seqs = seqs if seqs is not None else host_sample(a, n_sample)
     threads = orc.max_threads()
     t0 = time.perf_counter()
-    orc.fasta_dist(seqs, a.k, alphabet=orc.DNA, batch=20, threads=threads, mode=0)
+    orc.fasta_dist(seqs, a.k, alphabet=orc.DNA, batch=20, threads=threads, mode=mode)
     dt = time.perf_counter() - t0
     pairs = n_sample * (n_sample - 1) // 2
     return pairs / dt, dt, threads, pairs
+
+
+def cpu_phase_costs(a, seqs):
+    """single-thread cost of the two phases of the reference's algorithm (one set build, one probe)"""
+    from oracle import oracle as orc
+
+    t0 = time.perf_counter()
+    s0 = orc.StrSet(seqs[0], a.k)
+    t1 = time.perf_counter()
+    s1 = orc.StrSet(seqs[1], a.k)
+    t2 = time.perf_counter()
+    s0.similarity(s1)
+    t3 = time.perf_counter()
+    return {"set_build_s_per_genome_1thread": 0.5 * (t2 - t0), "probe_s_per_pair_1thread": t3 - t2,
+            "note": "HashSet<String> port; the reference pays one build per uncached column per pair plus one probe"}
+
+
+def cpu_baseline_block(a, value, dt, threads, pairs, extra=None):
+    sample = (f"first {a.cpu_sample} genomes of the workload ({pairs} pairs in {dt:.1f} s): reference decomposition, "
+              f"batch=20 cached serially, rows in parallel on {threads} threads, uncached columns rebuilt per pair; "
+              f"C port of the reference's HashSet<String> algorithm, not the JVM")
+    blk = {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
+           "pairs_per_s_per_core": value / max(threads, 1)}
+    if extra:
+        blk.update(extra)
+    return blk
 
 
 def reference_main(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
+    seqs = host_sample(a, a.cpu_sample)
     vals = []
     threads = pairs = 0
     for s in range(a.warmup + a.steps):
-        v, dt, threads, pairs = run_cpu_reference(a, a.cpu_sample)
+        v, dt, threads, pairs = run_cpu_reference(a, a.cpu_sample, seqs)
         if s >= a.warmup:
             vals.append((v, dt))
     value = sum(p for p, _ in vals) / len(vals)
     ms = 1e3 * sum(d for _, d in vals) / len(vals)
-    sample = (f"first {a.cpu_sample} genomes of the workload ({pairs} pairs/step), batch=20 so every set is cached "
-              f"(no per-pair rebuilds: favourable to the CPU); C port of the reference's HashSet<String> algorithm, "
-              f"not the JVM")
+    iv, idt, _, _ = run_cpu_reference(a, a.cpu_sample, seqs, mode=1)
+    extra = {"integer_mode": {"value": iv, "unit": UNIT, "seconds": idt,
+                              "what": "same sample and decomposition on sorted canonical uint64 sets with a linear merge "
+                                      "(not the reference's representation; shown so the string sets do not flatter the GPU)"},
+             "phases": cpu_phase_costs(a, seqs)}
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
             "warmup": a.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": "u64", "data": "synthetic", "config": {"workload": workload_name(a), "k": a.k},
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+            "dtype": "u64", "data": "synthetic", "config": config_dict(a, a.gpus),
+            "cpu_baseline": cpu_baseline_block(a, value, ms / 1e3, threads, pairs, extra),
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "gpu_launches": 0}
+            "gpu_launches": 0, "product_library_loaded": "genome.distance_b200" in sys.modules}
     print(json.dumps(line), flush=True)
     return 0
 
@@ -204,7 +251,6 @@ def main():
     N, Lg = a.genomes, a.length
     total_pairs = N * (N - 1) // 2
     my_ids = sharding.genome_slice(N, world, rank)
-    first_pair, n_my_pairs = sharding.pair_slice(total_pairs, world, rank)
 
     # synthetic inputs: this rank's genomes as text in HBM, and a pinned host copy for the e2e leg
     d_text = torch.empty((len(my_ids), Lg), dtype=torch.uint8, device=dev)
@@ -219,8 +265,16 @@ def main():
 
     eng = gkd.Engine(k=a.k, device=local)
     ext = torch.cuda.ExternalStream(eng.stream_ptr, device=dev)
-    inter = np.empty(n_my_pairs, dtype=np.uint64)
-    dist_out = np.empty(n_my_pairs, dtype=np.float64)
+    inter = np.empty(total_pairs if world == 1 else 0, dtype=np.uint64)
+    dist_out = np.empty(total_pairs if world == 1 else 0, dtype=np.float64)
+    check = {"pairs": 0, "inter_sum": 0, "related": 0}
+
+    def sink(gi, gj, bi, bd):
+        """every block of results lands in host arrays (inside the timed region); keep a checksum"""
+        bi = np.asarray(bi).reshape(-1)
+        check["pairs"] += bi.size
+        check["inter_sum"] += int(bi.sum(dtype=np.uint64))
+        check["related"] += int((np.asarray(bd).reshape(-1) < 1.0).sum())
 
     def one_step(text):
         """one pass of the hot path over the whole workload; returns engine metrics"""
@@ -231,20 +285,17 @@ def main():
         t_add = time.perf_counter()
         eng.build()
         t_build = time.perf_counter()
-        t_xchg = t_build
+        stats = {}
         if world > 1:
-            id_map = sharding.exchange_sets(eng, N, world, rank, dev)
-            torch.cuda.synchronize()
-            t_xchg = time.perf_counter()
-            ia, ib = sharding.local_pair_ids(id_map, N, first_pair, n_my_pairs)
-            eng.pairs(ia, ib, inter_out=inter, dist_out=dist_out)
+            check.update(pairs=0, inter_sum=0, related=0)
+            sharding.ring_all_vs_all(eng, N, world, rank, dev, panel_genomes=a.panel, sink=sink, stats=stats)
         else:
-            eng.all_vs_all_range(N, first_pair, n_my_pairs, inter_out=inter, dist_out=dist_out)
+            eng.all_vs_all_range(N, 0, total_pairs, inter_out=inter, dist_out=dist_out)
         m = eng.metrics()
         m["wall_add_ms"] = 1e3 * (t_add - t_start)
         m["wall_build_ms"] = 1e3 * (t_build - t_add)
-        m["wall_exchange_ms"] = 1e3 * (t_xchg - t_build)
-        m["wall_distance_ms"] = 1e3 * (time.perf_counter() - t_xchg)
+        m["wall_exchange_exposed_ms"] = 1e3 * stats.get("exposed_wait_s", 0.0)
+        m["wall_distance_ms"] = 1e3 * (time.perf_counter() - t_build)
         return m
 
     def barrier():
@@ -272,9 +323,8 @@ def main():
         return float(t[0]), float(t[1]), mets
 
     # warm-up (also sizes every pool), then the timed region with the clock sampler running
-    launches0 = None
     for _ in range(a.warmup):
-        m = one_step(d_text)
+        one_step(d_text)
     launches0 = eng.metrics()["launches"]
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
@@ -282,6 +332,11 @@ def main():
     dev_s, wall_s, mets = timed(d_text, a.steps)
     clocks = sampler.stop() if sampler else None
     launches = eng.metrics()["launches"] - launches0
+    if world > 1:
+        t = torch.tensor([float(launches), float(check["pairs"])], dtype=torch.float64, device=dev)
+        dist.all_reduce(t)
+        launches, pairs_done = int(t[0]), int(t[1])
+        assert pairs_done == total_pairs, (pairs_done, total_pairs)
 
     value = a.steps * total_pairs / dev_s
     ms_per_step = 1e3 * dev_s / a.steps
@@ -301,29 +356,42 @@ def main():
         e2e = {"value": a.steps * total_pairs / e_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * e_s / a.steps}
 
-    # roofline of the dominant kernel (k_intersect), from the engine's CUDA events on its own stream
+    # roofline of the dominant kernel (kernel 4), from the engine's CUDA events on its own stream, summed over
+    # the launches of a step (one launch at N=1; one per block of the ring at N>1); slowest rank at N>1
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(peaks_path):
         peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     else:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
-    isect_ms = sum(m["intersect_ms"] for m in mets) / len(mets)
-    isect_bytes = sum(m["intersect_bytes"] for m in mets) / len(mets)
+    isect_ms = sum(m["total_intersect_ms"] for m in mets) / len(mets)
+    isect_bytes = sum(m["total_intersect_bytes"] for m in mets) / len(mets)
+    if world > 1:
+        t = torch.tensor([isect_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        isect_ms = float(t[0])
     achieved = isect_bytes / (isect_ms * 1e-3) / 1e9 if isect_ms > 0 else 0.0
-    traffic = None
+    traffic, traffic_src, stored = None, None, None
     tpath = os.path.join(ROOT, "profiles", "intersect_traffic.json")
     if os.path.exists(tpath):
         try:
             tj = json.load(open(tpath))
-            # measured DRAM bytes per algorithmic byte on the profiled launch, scaled to this launch
             traffic = tj["dram_bytes_per_algorithmic_byte"] * isect_bytes
+            traffic_src = ("ESTIMATED, not measured in this run: ncu dram__bytes_read+write per algorithmic byte of the "
+                           f"profiled launch ({tj.get('source', 'profiles/')}) x this run's algorithmic bytes")
+            stored = tj.get("stored_bytes_per_algorithmic_byte")
         except Exception:
             traffic = None
-    kname = {0: "k_intersect<IsectCfg<192,17,9,3>> (CTA merge path)", 1: "k_intersect_warp", 2: "k_intersect_small"}
-    roofline = {"kernel": kname.get(int(mets[-1].get("intersect_kernel", 0)), "k_intersect"), "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": isect_bytes, "ms_per_launch": isect_ms,
-                "note": "achieved = 8*(|A|+|B|) bytes per pair / CUDA-event time; rows served from L2 can push it past HBM peak"}
+    kname = {3: "k_intersect_bucket<uint32_t> (bucket merge, 32-bit low words)",
+             4: "k_intersect_bucket<uint64_t> (bucket merge, 64-bit keys)"}
+    roofline = {"kernel": kname.get(int(mets[-1].get("intersect_kernel", 0)), "k_intersect_bucket"), "bound": "hbm",
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                "traffic_source": traffic_src, "peak_source": peak_src,
+                "algorithmic_bytes_per_step": isect_bytes, "ms_per_step": isect_ms,
+                "note": "achieved = 8*(|A|+|B|) bytes per pair (SURVEY 8d definition: sorted uint64 sets) / CUDA-event time "
+                        "of kernel 4.  The kernel reads the sets in a compressed layout (32-bit low words + bucket table, "
+                        "~4.25 stored bytes per key) and the row sets are served from L2, so the algorithmic figure can "
+                        "exceed the HBM peak; stored_frac is the same fraction on the bytes actually stored",
+                "stored_frac": (achieved / peak) * stored if stored else None}
     build_ms = sum(m["encode_ms"] + m["sort_ms"] + m["unique_ms"] for m in mets) / len(mets)
     kpos = sum(m["kmer_positions"] for m in mets) / len(mets)
     stages = {"encode_ms": sum(m["encode_ms"] for m in mets) / len(mets),
@@ -333,26 +401,52 @@ def main():
               "kmers_hashed_per_s_this_rank": kpos / (build_ms * 1e-3) if build_ms > 0 else 0.0,
               "sort_passes": mets[-1]["sort_passes"],
               "wall_ms": {k: sum(m[k] for m in mets) / len(mets) for k in
-                          ("wall_add_ms", "wall_build_ms", "wall_exchange_ms", "wall_distance_ms")}}
+                          ("wall_add_ms", "wall_build_ms", "wall_exchange_exposed_ms", "wall_distance_ms")}}
 
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
-        v, dt, threads, pairs = run_cpu_reference(a, a.cpu_sample)
-        cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
-               "sample": f"first {a.cpu_sample} genomes of the workload, {pairs} pairs in {dt:.1f} s; HashSet<String> port "
-                         f"of FastaDistanceProcessor (batch=20, all sets cached: favourable to the CPU); not the JVM"}
+        seqs = host_sample(a, a.cpu_sample)
+        v, dt, threads, pairs = run_cpu_reference(a, a.cpu_sample, seqs)
+        iv, idt, _, _ = run_cpu_reference(a, a.cpu_sample, seqs, mode=1)
+        cpu = cpu_baseline_block(a, v, dt, threads, pairs,
+                                 {"integer_mode": {"value": iv, "unit": UNIT, "seconds": idt,
+                                                   "what": "same sample and decomposition on sorted canonical uint64 sets "
+                                                           "with a linear merge (not the reference's representation)"},
+                                  "phases": cpu_phase_costs(a, seqs)})
+
+    other = None
+    if a.other_configs and world == 1:
+        eng.close()
+        eng = None
+        del d_text, h_text
+        torch.cuda.empty_cache()
+        from tools import run_config
+
+        other = []
+        for fn in (run_config.c1, lambda: run_config.c3(10000, 500, 4000), lambda: run_config.c5(2000)):
+            try:
+                other.append(fn())
+            except Exception as ex:  # a failed side config must not lose the headline line
+                other.append({"error": repr(ex)})
 
     if rank == 0:
+        cfg = config_dict(a, world)
+        cfg["sharding"] = (f"rank blocks of the pair matrix x{world}, peers' sets arrive as panels of <= {a.panel} sets "
+                           "over NCCL send/recv, overlapped with kernel 4") if world > 1 else "single GPU"
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-                "dtype": "u64", "data": "synthetic",
-                "config": {"workload": workload_name(a), "k": a.k, "genomes": N, "genome_bp": Lg, "pairs": total_pairs,
-                           "families": a.families, "sharding": f"pair-range x{world}" if world > 1 else "single GPU",
-                           "l2": "inputs (40 MB per set, 40 GB total) are far larger than L2; no flush needed"},
+                "dtype": "u64", "data": "synthetic", "config": cfg,
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
                 "clocks": clocks, "stages": stages, "wall_s_timed_region": wall_s}
+        if world > 1:
+            line["critical_path_collective"] = ("none in steady state: each panel's send/recv is posted before the kernels of "
+                                                "the previous panel; exposed wait per step = stages.wall_ms.wall_exchange_exposed_ms")
+            line["checksum"] = {"pairs": total_pairs, "related_pairs_this_rank": check["related"]}
+        if other is not None:
+            line["other_configs"] = other
         print(json.dumps(line), flush=True)
-    eng.close()
+    if eng is not None:
+        eng.close()
     if world > 1:
         dist.destroy_process_group()
     return 0

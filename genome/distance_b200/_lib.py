@@ -11,11 +11,24 @@ LIB_PATH = os.environ.get("GKD_LIB") or os.path.join(_HERE, "libgkd.so")  # GKD_
 GKD_OK, GKD_EINVAL, GKD_EIO, GKD_ENOMEM, GKD_ECUDA, GKD_ESTATE = 0, -1, -2, -3, -4, -5
 DNA, PROT, RNA = 0, 1, 2
 STRAND_BOTH, STRAND_CANONICAL = 0, 1
+AMBIG_SKIP, AMBIG_LITERAL = 0, 1
+ABI_VERSION = 2
 
 
 class GkdConfig(C.Structure):
     _fields_ = [("device", C.c_int32), ("k", C.c_int32), ("alphabet", C.c_int32), ("strand_mode", C.c_int32),
-                ("workspace_bytes", C.c_uint64), ("segment_keys", C.c_uint32), ("reserved", C.c_uint32 * 7)]
+                ("workspace_bytes", C.c_uint64), ("segment_keys", C.c_uint32), ("ambig_policy", C.c_int32),
+                ("reserved", C.c_uint32 * 6)]
+
+
+class GkdPackedSet(C.Structure):
+    _fields_ = [("offs_off", C.c_uint64), ("lows_off", C.c_uint64), ("pal_offs_off", C.c_uint64),
+                ("pal_lows_off", C.c_uint64), ("n", C.c_uint32), ("n_pal", C.c_uint32), ("level", C.c_uint32),
+                ("pal_level", C.c_uint32)]
+
+
+class GkdOutputs(C.Structure):
+    _fields_ = [("inter", C.c_void_p), ("dist", C.c_void_p), ("contain_a", C.c_void_p), ("contain_b", C.c_void_p)]
 
 
 class GkdMetrics(C.Structure):
@@ -24,7 +37,8 @@ class GkdMetrics(C.Structure):
                 ("residues_packed", C.c_uint64), ("kmer_positions", C.c_uint64), ("keys_sorted", C.c_uint64),
                 ("sort_passes", C.c_uint32), ("intersect_kernel", C.c_uint32), ("keys_unique", C.c_uint64), ("pairs", C.c_uint64),
                 ("intersect_bytes", C.c_uint64), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64),
-                ("launches", C.c_uint64), ("intersect_launches", C.c_uint64), ("reserved", C.c_uint64 * 6)]
+                ("launches", C.c_uint64), ("intersect_launches", C.c_uint64), ("total_pairs", C.c_uint64),
+                ("total_intersect_bytes", C.c_uint64), ("total_intersect_ms", C.c_double), ("reserved", C.c_uint64 * 3)]
 
 
 # every symbol include/gkd.h declares: name -> (restype, argtypes)
@@ -45,7 +59,10 @@ SYMBOLS = {
     "gkd_build_sets": (_i32, [_vp]),
     "gkd_set_size": (_i32, [_vp, _u32, _pu64, _pu64, _pu64]),
     "gkd_export_set": (_i32, [_vp, _u32, _vp, _u64, _pu64]),
-    "gkd_set_device_ptr": (_i32, [_vp, _u32, C.POINTER(_vp), _pu64]),
+    "gkd_arena_count": (_u32, [_vp]),
+    "gkd_arena_info": (_i32, [_vp, _u32, _pu32, _pu32, C.POINTER(_vp), _pu64]),
+    "gkd_describe_sets": (_i32, [_vp, _u32, _u32, C.POINTER(GkdPackedSet)]),
+    "gkd_adopt_sets": (_i32, [_vp, _vp, _u64, C.POINTER(GkdPackedSet), _u32, _pu32]),
     "gkd_import_set": (_i32, [_vp, _vp, _u64, _pu32]),
     "gkd_import_sets": (_i32, [_vp, _vp, _pu64, _u32, _pu32]),
     "gkd_save_sets": (_i32, [_vp, C.c_char_p]),
@@ -54,6 +71,9 @@ SYMBOLS = {
     "gkd_all_vs_all_range": (_i32, [_vp, _u32, _u64, _u64, _vp, _vp]),
     "gkd_query_vs_ref": (_i32, [_vp, _vp, _u32, _vp, _u32, _vp, _vp]),
     "gkd_pairs": (_i32, [_vp, _vp, _vp, _u64, _vp, _vp]),
+    "gkd_all_vs_all_range_ex": (_i32, [_vp, _u32, _u64, _u64, C.POINTER(GkdOutputs)]),
+    "gkd_query_vs_ref_ex": (_i32, [_vp, _vp, _u32, _vp, _u32, C.POINTER(GkdOutputs)]),
+    "gkd_pairs_ex": (_i32, [_vp, _vp, _vp, _u64, C.POINTER(GkdOutputs)]),
     "gkd_pair": (_i32, [_vp, _u32, _u32, _pu64, _pu64, _pdbl]),
     "gkd_format_double": (_i32, [_dbl, C.c_char_p, C.c_size_t]),
     "gkd_get_metrics": (_i32, [_vp, C.POINTER(GkdMetrics)]),

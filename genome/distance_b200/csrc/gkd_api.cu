@@ -2,6 +2,7 @@
 // One context = one CUDA device, one stream.  No CPU fallback: without a usable device every
 // computing entry point fails with GKD_ECUDA.
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>
 
 #include <algorithm>
 #include <cmath>
@@ -9,7 +10,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <new>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "gkd_internal.cuh"
@@ -37,6 +40,7 @@ constexpr uint64_t STAGE_BYTES = 32ull << 20;  // text staged per piece (multipl
 constexpr int N_STAGE = 3;
 constexpr uint64_t DEFAULT_WORKSPACE = 8ull << 30;
 constexpr uint64_t PAIR_CHUNK = 64ull << 20;  // pairs per distance launch
+constexpr uint64_t SET_BLOCK_ALIGN = 256;     // every set block of an arena starts on this boundary
 
 struct Part {  // a run of residue text; new_contig starts a new contig (k-mers do not span contigs)
     const char *ptr;
@@ -50,7 +54,10 @@ struct GenomeRec {
     void *d_codes = nullptr;    // packed stream (slab memory)
     uint32_t *d_mask = nullptr;
     bool built = false;
-    SetDesc desc{nullptr, 0, 0, nullptr};
+    SetDesc desc{{nullptr, nullptr, 0, 0}, {nullptr, nullptr, 0, 0}};
+    gkd_packed_set packed{};    // layout relative to the base of `arena`
+    int arena = -1;
+    std::vector<uint32_t> lit;  // GKD_AMBIG_LITERAL: sorted ids (context dictionary) of the literal k-mers
 };
 
 struct Slab {
@@ -63,12 +70,29 @@ struct DevBuf {  // grow-only scratch buffer
     uint64_t cap = 0;
 };
 
+struct Arena {  // finished sets of one build / import batch, or an adopted buffer
+    char *base;
+    uint64_t bytes;  // bytes in use (owned: <= capacity)
+    uint64_t capacity;
+    uint32_t first_id, n_sets;
+    bool owned;
+};
+
+struct NvtxRange {
+    explicit NvtxRange(const char *name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+};
+
 }  // namespace
 
 struct gkd_ctx {
     gkd_config cfg{};
     int k = 0;
     int n_sms = 148;
+    int key_bits = 0, low_bits = 32;
+    uint32_t lvl_min = 0;
+    uint32_t table_tmax = 16, isect_tmax = 16;
+    MixParams mix{};
     cudaStream_t stream = nullptr;
     bool poisoned = false;
     std::string err;
@@ -77,18 +101,19 @@ struct gkd_ctx {
     uint32_t built_upto = 0;
 
     std::vector<Slab> slabs;
-    std::vector<std::pair<void *, uint64_t>> set_arenas;   // live set arenas (ptr, bytes)
-    std::vector<uint32_t> arena_first_id;                   // first set id stored in each live arena
-    std::vector<std::pair<void *, uint64_t>> free_arenas;  // arenas released by gkd_reset, reused best-fit
+    std::vector<Arena> arenas;                              // live, in id order
+    std::vector<std::pair<void *, uint64_t>> free_arenas;  // owned arenas released by reset/truncate, reused best-fit
 
     char *bounce[N_STAGE] = {nullptr, nullptr, nullptr};
     cudaEvent_t bounce_ev[N_STAGE] = {nullptr, nullptr, nullptr};
     char *stage_dev[N_STAGE] = {nullptr, nullptr, nullptr};
     int stage_next = 0;
 
-    DevBuf keys_a, keys_b, tile_hist, tile_uniq, genome_counts, batch_genomes, uniq_dst;
-    DevBuf d_sets, counts, pal_counts, d_inter, d_dist, ids_a, ids_b, work_counter;
+    DevBuf keys_a, keys_b, tile_hist, tile_uniq, genome_counts, batch_genomes, set_build;
+    DevBuf d_sets, counts, pal_counts, d_inter, d_dist, d_ca, d_cb, ids_a, ids_b, work_counter;
     bool sets_dirty = true;
+
+    std::unordered_map<std::string, uint32_t> lit_dict;  // GKD_AMBIG_LITERAL: literal k-mer -> dense id
 
     cudaEvent_t ev[8] = {};
     gkd_metrics m{};
@@ -122,6 +147,13 @@ int fail(gkd_ctx *c, int code, const char *fmt, ...) {
         if (!(c)) return GKD_EINVAL;                                                   \
         if ((c)->poisoned) return fail((c), GKD_ECUDA, "context poisoned by an earlier CUDA error: %s", (c)->err.c_str()); \
     } while (0)
+
+// no C++ exception may cross the ABI (gkd.h): bodies that allocate host memory run inside this guard
+#define ABI_GUARD_BEGIN try {
+#define ABI_GUARD_END(c)                                                        \
+    }                                                                           \
+    catch (const std::bad_alloc &) { return fail((c), GKD_ENOMEM, "out of host memory"); } \
+    catch (const std::exception &ex__) { return fail((c), GKD_EINVAL, "internal error: %s", ex__.what()); }
 
 int ensure(gkd_ctx *c, DevBuf &b, uint64_t bytes) {
     if (bytes <= b.cap) return GKD_OK;
@@ -176,9 +208,100 @@ double elapsed(cudaEvent_t a, cudaEvent_t b) {
     return ms;
 }
 
+// ---- GKD_AMBIG_LITERAL: literal k-mers of one genome (host side) ----------------------------------------
+// Restates the recalled upstream behaviour ("low / unpinned"): the lower-cased window that
+// holds a character outside acgt is a set member as a literal string, and so is the window of the reverse
+// complement strand, where the complement of an unknown base is 'n'.  These strings can never equal a
+// pure-acgt k-mer, so they form a side set that is disjoint from the canonical keys.  They are rare
+// (2(K-1)+1 distinct strings per run of unknown bases), so each genome keeps the sorted ids of its
+// strings in a per-context dictionary and pairs are completed on the host.
+inline char fold_nuc(char ch, bool rna) {
+    if (ch >= 'A' && ch <= 'Z') ch = (char)(ch + 32);
+    if (rna && ch == 'u') ch = 't';
+    return ch;
+}
+inline char complement_nuc(char ch) {
+    switch (ch) {
+    case 'a': return 't';
+    case 'c': return 'g';
+    case 'g': return 'c';
+    case 't': return 'a';
+    default: return 'n';
+    }
+}
+
+void literal_kmers_of_contig(gkd_ctx *c, const std::string &ct, std::vector<uint32_t> &ids) {
+    const size_t k = (size_t)c->k, len = ct.size();
+    if (len < k) return;
+    std::string fwd(k, ' '), rc(k, ' ');
+    size_t next_w = 0;  // first window start not yet emitted
+    for (size_t p = 0; p < len; p++) {
+        const char ch = ct[p];
+        if (ch == 'a' || ch == 'c' || ch == 'g' || ch == 't') continue;
+        size_t w0 = p + 1 >= k ? p + 1 - k : 0, w1 = std::min(p, len - k);
+        if (w0 < next_w) w0 = next_w;
+        for (size_t w = w0; w <= w1; w++) {
+            for (size_t i = 0; i < k; i++) {
+                fwd[i] = ct[w + i];
+                rc[i] = complement_nuc(ct[w + k - 1 - i]);
+            }
+            for (const std::string *s : {&fwd, &rc}) {
+                auto it = c->lit_dict.find(*s);
+                uint32_t id;
+                if (it == c->lit_dict.end()) {
+                    id = (uint32_t)c->lit_dict.size();
+                    c->lit_dict.emplace(*s, id);
+                } else id = it->second;
+                ids.push_back(id);
+            }
+        }
+        if (w1 + 1 > next_w) next_w = w1 + 1;
+    }
+}
+
+int collect_literals(gkd_ctx *c, const std::vector<Part> &parts, MemKind kind, std::vector<uint32_t> &ids) {
+    const bool rna = c->cfg.alphabet == GKD_RNA;
+    std::string ct;
+    std::vector<char> tmp;
+    auto flush = [&]() {
+        if (!ct.empty()) literal_kmers_of_contig(c, ct, ids);
+        ct.clear();
+    };
+    for (size_t i = 0; i < parts.size(); i++) {
+        const Part &p = parts[i];
+        if (p.new_contig) flush();
+        const char *src = p.ptr;
+        if (kind == MEM_DEVICE && p.len) {
+            tmp.resize(p.len);
+            CK(cudaMemcpyAsync(tmp.data(), p.ptr, p.len, cudaMemcpyDeviceToHost, c->stream));
+            CK(cudaStreamSynchronize(c->stream));
+            src = tmp.data();
+        }
+        const size_t at = ct.size();
+        ct.resize(at + p.len);
+        for (uint64_t j = 0; j < p.len; j++) ct[at + j] = fold_nuc(src[j], rna);
+    }
+    flush();
+    std::sort(ids.begin(), ids.end());
+    ids.erase(std::unique(ids.begin(), ids.end()), ids.end());
+    return GKD_OK;
+}
+
+uint64_t literal_intersection(const std::vector<uint32_t> &a, const std::vector<uint32_t> &b) {
+    uint64_t n = 0;
+    size_t i = 0, j = 0;
+    while (i < a.size() && j < b.size()) {
+        if (a[i] < b[j]) i++;
+        else if (b[j] < a[i]) j++;
+        else n++, i++, j++;
+    }
+    return n;
+}
+
 // ---- ingest -------------------------------------------------------------------------------------------
 int add_genome(gkd_ctx *c, const std::vector<Part> &parts, const std::string &label, const std::string &comment,
                uint32_t *out_id) {
+    NvtxRange nvtx("gkd kernel 1: ingest + pack");
     const bool prot = c->cfg.alphabet == GKD_PROT;
     uint64_t n_pos = 0;
     bool first = true;
@@ -208,6 +331,7 @@ int add_genome(gkd_ctx *c, const std::vector<Part> &parts, const std::string &la
         if (parts.size() > 1 && classify(parts.back().ptr) != kind)
             return fail(c, GKD_EINVAL, "all sequence pieces of one call must be in the same kind of memory");
     }
+    if (!prot && c->cfg.ambig_policy == GKD_AMBIG_LITERAL && (rc = collect_literals(c, parts, kind, g.lit))) return rc;
     // walk the stream in pieces of at most STAGE_BYTES positions
     size_t pi = 0;          // current part
     uint64_t pofs = 0;      // offset inside current part
@@ -276,9 +400,9 @@ int add_genome(gkd_ctx *c, const std::vector<Part> &parts, const std::string &la
         c->m.launches++;
         q0 = q1;
     } while (q0 < n_pos);
-    // contract (gkd.h): inputs are consumed before the call returns.  Pageable text was copied into the
-    // bounce buffers synchronously; pinned/device text is read by stream-ordered copies, so wait for them.
-    if (kind != MEM_PAGEABLE) CK(cudaStreamSynchronize(c->stream));
+    // contract (gkd.h): pageable text was copied into the bounce buffers before this returns; pinned and
+    // device text is read by the stream-ordered copies above and must stay valid until gkd_build_sets
+    // (which synchronises) -- no per-genome synchronisation here.
     c->m.residues_packed += n_pos;
     if (out_id) *out_id = (uint32_t)c->genomes.size();
     c->genomes.push_back(std::move(g));
@@ -286,68 +410,109 @@ int add_genome(gkd_ctx *c, const std::vector<Part> &parts, const std::string &la
 }
 
 // ---- set construction ------------------------------------------------------------------------------------
-struct BatchItem {
-    uint32_t id;        // genome index, or UINT32_MAX for an imported key array
-    uint32_t n_slots;
-};
+bool has_pal_lists(const gkd_ctx *c) { return c->cfg.alphabet != GKD_PROT && (c->k % 2 == 0); }
+
+// device allocation for a batch of finished sets: best-fitting parked arena, else a fresh one (parked
+// arenas that were too small are released first so a streamed run does not creep up in memory)
+int arena_alloc(gkd_ctx *c, uint64_t need, void **out, uint64_t *cap) {
+    int best = -1;
+    for (size_t i = 0; i < c->free_arenas.size(); i++)
+        if (c->free_arenas[i].second >= need && (best < 0 || c->free_arenas[i].second < c->free_arenas[best].second))
+            best = (int)i;
+    if (best >= 0) {
+        *out = c->free_arenas[best].first;
+        *cap = c->free_arenas[best].second;
+        c->free_arenas.erase(c->free_arenas.begin() + best);
+        return GKD_OK;
+    }
+    for (auto &a : c->free_arenas) CK(cudaFreeAsync(a.first, c->stream));
+    c->free_arenas.clear();
+    CK(cudaMallocAsync(out, need, c->stream));
+    *cap = need;
+    return GKD_OK;
+}
+
+void set_desc_from_packed(GenomeRec &g, const char *base) {
+    const gkd_packed_set &p = g.packed;
+    g.desc.main.offs = (const uint32_t *)(base + p.offs_off);
+    g.desc.main.lows = base + p.lows_off;
+    g.desc.main.n = p.n;
+    g.desc.main.level = p.level;
+    const bool pal = p.pal_offs_off != 0 || p.pal_lows_off != 0;
+    g.desc.pal.offs = pal ? (const uint32_t *)(base + p.pal_offs_off) : nullptr;
+    g.desc.pal.lows = pal ? base + p.pal_lows_off : nullptr;
+    g.desc.pal.n = p.n_pal;
+    g.desc.pal.level = p.pal_level;
+}
 
 // unique/compact the sorted slots of a batch into a fresh set arena and record the descriptors
 int finish_batch(gkd_ctx *c, const std::vector<BatchGenome> &bg, const std::vector<uint32_t> &ids, const SortPlan &plan,
                  const uint64_t *sorted) {
     const uint32_t n = (uint32_t)bg.size();
-    CK(launch_unique_count((const BatchGenome *)c->batch_genomes.p, plan, sorted, c->cfg.alphabet, c->k, c->stream));
+    CK(launch_unique_count((const BatchGenome *)c->batch_genomes.p, plan, sorted, c->cfg.alphabet, c->k, c->mix, c->stream));
     c->m.launches += 2;
     std::vector<uint64_t> counts(n);
     CK(cudaMemcpyAsync(counts.data(), plan.genome_counts, n * sizeof(uint64_t), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
-    uint64_t arena_keys = 0;
+    const bool pal = has_pal_lists(c);
+    const uint64_t lsz = c->low_bits / 8;
+    // layout: per set [offs][lows][pal offs][pal lows][pal scratch], every piece a multiple of 16 bytes
+    std::vector<gkd_packed_set> packed(n);
+    std::vector<uint64_t> palh_off(n, 0);
+    uint64_t cur = 0;
     for (uint32_t i = 0; i < n; i++) {
-        uint32_t nu = (uint32_t)counts[i], np = (uint32_t)(counts[i] >> 32);
-        arena_keys += set_padded(nu);
-        if (np) arena_keys += set_padded(np);
+        gkd_packed_set &p = packed[i];
+        p = gkd_packed_set{};
+        p.n = (uint32_t)counts[i];
+        p.n_pal = (uint32_t)(counts[i] >> 32);
+        p.level = set_level(p.n, c->table_tmax, c->key_bits, c->low_bits);
+        cur = (cur + SET_BLOCK_ALIGN - 1) & ~(SET_BLOCK_ALIGN - 1);
+        p.offs_off = cur;
+        cur += align16(((1ull << p.level) + 1) * 4);
+        p.lows_off = cur;
+        cur += align16((uint64_t)p.n * lsz) + 16;
+        if (pal) {
+            p.pal_level = set_level(p.n_pal, c->table_tmax, c->key_bits, c->low_bits);
+            p.pal_offs_off = cur;
+            cur += align16(((1ull << p.pal_level) + 1) * 4);
+            p.pal_lows_off = cur;
+            cur += align16((uint64_t)p.n_pal * lsz) + 16;
+            palh_off[i] = cur;
+            cur += align16((uint64_t)p.n_pal * 8);
+        }
     }
+    const uint64_t need = cur + 256;
     void *arena = nullptr;
-    {
-        // reuse an arena released by gkd_reset (best fit) so repeated runs do not make the pool remap
-        const uint64_t need = arena_keys * 8 + 256;
-        int best = -1;
-        for (size_t i = 0; i < c->free_arenas.size(); i++)
-            if (c->free_arenas[i].second >= need && (best < 0 || c->free_arenas[i].second < c->free_arenas[best].second))
-                best = (int)i;
-        if (best >= 0) {
-            arena = c->free_arenas[best].first;
-            c->set_arenas.push_back(c->free_arenas[best]);
-            c->free_arenas.erase(c->free_arenas.begin() + best);
-        } else {
-            CK(cudaMallocAsync(&arena, need, c->stream));
-            c->set_arenas.push_back({arena, need});
-        }
-        c->arena_first_id.push_back(ids.empty() ? 0u : ids.front());
-    }
-    std::vector<UniqueDst> dst(n);
-    uint64_t *cur = (uint64_t *)arena;
-    for (uint32_t i = 0; i < n; i++) {
-        uint32_t nu = (uint32_t)counts[i], np = (uint32_t)(counts[i] >> 32);
-        dst[i].keys = cur;
-        cur += set_padded(nu);
-        dst[i].pal_keys = nullptr;
-        if (np) {
-            dst[i].pal_keys = cur;
-            cur += set_padded(np);
-        }
-        GenomeRec &g = c->genomes[ids[i]];
-        g.desc.keys = dst[i].keys;
-        g.desc.n = nu;
-        g.desc.n_pal = np;
-        g.desc.pal_keys = dst[i].pal_keys;
-        g.built = true;
-        c->m.keys_unique += nu;
-    }
-    int rc = ensure(c, c->uniq_dst, n * sizeof(UniqueDst));
+    uint64_t cap = 0;
+    int rc = arena_alloc(c, need, &arena, &cap);
     if (rc) return rc;
-    CK(cudaMemcpyAsync(c->uniq_dst.p, dst.data(), n * sizeof(UniqueDst), cudaMemcpyHostToDevice, c->stream));
-    CK(launch_unique_write((const BatchGenome *)c->batch_genomes.p, plan, sorted, (const UniqueDst *)c->uniq_dst.p,
-                           c->cfg.alphabet, c->k, c->stream));
+    c->arenas.push_back(Arena{(char *)arena, need, cap, ids.empty() ? 0u : ids.front(), n, true});
+    const int arena_idx = (int)c->arenas.size() - 1;
+    std::vector<SetBuild> dst(n);
+    char *base = (char *)arena;
+    for (uint32_t i = 0; i < n; i++) {
+        const gkd_packed_set &p = packed[i];
+        SetBuild &d = dst[i];
+        d.offs = (uint32_t *)(base + p.offs_off);
+        d.lows = base + p.lows_off;
+        d.n = p.n;
+        d.level = p.level;
+        d.n_pal = p.n_pal;
+        d.pal_level = p.pal_level;
+        d.pal_offs = pal ? (uint32_t *)(base + p.pal_offs_off) : nullptr;
+        d.pal_lows = pal ? (void *)(base + p.pal_lows_off) : nullptr;
+        d.pal_h = pal ? (uint64_t *)(base + palh_off[i]) : nullptr;
+        GenomeRec &g = c->genomes[ids[i]];
+        g.packed = p;
+        g.arena = arena_idx;
+        set_desc_from_packed(g, base);
+        g.built = true;
+        c->m.keys_unique += p.n;
+    }
+    if ((rc = ensure(c, c->set_build, n * sizeof(SetBuild)))) return rc;
+    CK(cudaMemcpyAsync(c->set_build.p, dst.data(), n * sizeof(SetBuild), cudaMemcpyHostToDevice, c->stream));
+    CK(launch_unique_write((const BatchGenome *)c->batch_genomes.p, plan, sorted, (const SetBuild *)c->set_build.p,
+                           c->cfg.alphabet, c->k, c->mix, c->low_bits, c->stream));
     c->m.launches += 2;
     // the host vectors above are pageable: make sure the copies were consumed before they die
     CK(cudaStreamSynchronize(c->stream));
@@ -366,7 +531,7 @@ int plan_batch(gkd_ctx *c, std::vector<BatchGenome> &bg, SortPlan &plan, uint64_
     CK(cudaMemcpyAsync(c->batch_genomes.p, bg.data(), bg.size() * sizeof(BatchGenome), cudaMemcpyHostToDevice, c->stream));
     plan.n_genomes = (uint32_t)bg.size();
     plan.n_tiles = n_tiles;
-    plan.key_bits = c->cfg.alphabet == GKD_PROT ? 8 * c->k : 2 * c->k;
+    plan.key_bits = c->key_bits;
     plan.keys_a = (uint64_t *)c->keys_a.p;
     plan.keys_b = (uint64_t *)c->keys_b.p;
     plan.tile_hist = (uint32_t *)c->tile_hist.p;
@@ -400,18 +565,25 @@ int build_batch(gkd_ctx *c, uint32_t first, uint32_t last) {
     int rc = plan_batch(c, bg, plan, std::max<uint64_t>(raw, 16), tiles);
     if (rc) return rc;
     CK(cudaEventRecord(c->ev[0], c->stream));
-    CK(launch_encode((const BatchGenome *)c->batch_genomes.p, plan.n_genomes, tiles, c->cfg.alphabet, c->k, plan.keys_a,
-                     c->stream));
+    nvtxRangePushA("gkd kernel 2: canonical encode + mix");
+    CK(launch_encode((const BatchGenome *)c->batch_genomes.p, plan.n_genomes, tiles, c->cfg.alphabet, c->k, c->mix,
+                     plan.keys_a, c->stream));
+    nvtxRangePop();
     if (tiles) c->m.launches++;
     CK(cudaEventRecord(c->ev[1], c->stream));
     uint64_t *sorted = nullptr;
     uint32_t passes = 0;
+    nvtxRangePushA("gkd kernel 3: radix sort");
     CK(launch_sort((const BatchGenome *)c->batch_genomes.p, plan, &sorted, &passes, c->stream));
+    nvtxRangePop();
     c->m.launches += 3ull * passes;
     c->m.sort_passes = passes;
     c->m.keys_sorted += raw;
     CK(cudaEventRecord(c->ev[2], c->stream));
-    rc = finish_batch(c, bg, ids, plan, sorted);
+    {
+        NvtxRange nvtx("gkd kernel 3: unique + bucket tables");
+        rc = finish_batch(c, bg, ids, plan, sorted);
+    }
     if (rc) return rc;
     CK(cudaEventRecord(c->ev[3], c->stream));
     CK(cudaStreamSynchronize(c->stream));
@@ -434,6 +606,44 @@ int upload_sets(gkd_ctx *c) {
     return GKD_OK;
 }
 
+// adopt key arrays (device memory, back to back at offsets[]) as new sets: mix, sort, unique
+int import_device_batch(gkd_ctx *c, const uint64_t *keys, const uint64_t *offsets, uint32_t i0, uint32_t i1, bool on_device) {
+    const uint32_t id0 = (uint32_t)c->genomes.size();
+    std::vector<BatchGenome> bg(i1 - i0);
+    std::vector<uint32_t> ids(i1 - i0);
+    uint32_t tiles = 0;
+    const uint64_t k0 = offsets[i0], total = offsets[i1] - k0;
+    for (uint32_t i = i0; i < i1; i++) {
+        BatchGenome &b = bg[i - i0];
+        b.codes = nullptr;
+        b.mask = nullptr;
+        b.raw_off = offsets[i] - k0;
+        b.n_pos = 0;
+        b.n_slots = (uint32_t)(offsets[i + 1] - offsets[i]);
+        b.tile_first = tiles;
+        b.n_tiles = (b.n_slots + SORT_TILE - 1) / SORT_TILE;
+        tiles += b.n_tiles;
+        ids[i - i0] = id0 + (i - i0);
+    }
+    SortPlan plan{};
+    int rc = plan_batch(c, bg, plan, std::max<uint64_t>(total, 16), tiles);
+    if (rc) return rc;
+    if (total) {
+        CK(cudaMemcpyAsync(plan.keys_a, keys + k0, total * 8, cudaMemcpyDefault, c->stream));
+        if (!on_device) c->m.h2d_bytes += total * 8;
+        CK(launch_mix_keys(plan.keys_a, total, c->mix, c->stream));
+        c->m.launches++;
+    }
+    uint64_t *sorted = nullptr;
+    uint32_t passes = 0;
+    CK(launch_sort((const BatchGenome *)c->batch_genomes.p, plan, &sorted, &passes, c->stream));
+    c->m.launches += 3ull * passes;
+    for (uint32_t i = i0; i < i1; i++) c->genomes.push_back(GenomeRec());
+    rc = finish_batch(c, bg, ids, plan, sorted);
+    if (rc) c->genomes.resize(id0);
+    return rc;
+}
+
 // ---- distances ------------------------------------------------------------------------------------------
 // host copy of the pair source (ids live on the host here)
 struct HostPairs {
@@ -450,7 +660,29 @@ int check_built(gkd_ctx *c, uint32_t id) {
     return GKD_OK;
 }
 
-int run_pairs(gkd_ctx *c, const HostPairs &hp, uint64_t *inter, double *dist) {
+// SequenceKmers.distance on the host, for the pairs the literal side lists complete (same double formula
+// as kernel 5)
+double host_distance(uint64_t I, uint64_t sa, uint64_t sb) {
+    double ret = 1.0, similarity = (double)I;
+    if (similarity > 0) {
+        int32_t sum = (int32_t)((uint32_t)sa + (uint32_t)sb);
+        ret = 1.0 - similarity / ((double)sum - similarity);
+    }
+    return ret;
+}
+
+uint64_t both_size(const gkd_ctx *c, const GenomeRec &g) {
+    const bool both = c->cfg.alphabet != GKD_PROT && c->cfg.strand_mode == GKD_STRAND_BOTH;
+    return (both ? 2ull * g.desc.main.n - g.desc.pal.n : g.desc.main.n) + g.lit.size();
+}
+
+void host_pair_ids(const HostPairs &hp, uint64_t t, uint32_t &a, uint32_t &b) {
+    if (hp.mode == PAIRS_UPPER) upper_pair(hp.first + t, hp.n, a, b);
+    else if (hp.mode == PAIRS_RECT) a = hp.a[t / hp.nb], b = hp.b[t % hp.nb];
+    else a = hp.a[t], b = hp.b[t];
+}
+
+int run_pairs(gkd_ctx *c, const HostPairs &hp, const gkd_outputs &out) {
     int rc = upload_sets(c);
     if (rc) return rc;
     const bool nuc = c->cfg.alphabet != GKD_PROT;
@@ -460,15 +692,24 @@ int run_pairs(gkd_ctx *c, const HostPairs &hp, uint64_t *inter, double *dist) {
     c->m.intersect_bytes = 0;
     c->m.intersect_ms = c->m.epilogue_ms = 0;
 
-    // validate ids, gather sizes for the segmenting decision and the byte accounting
-    uint64_t max_n = 0, min_n = UINT64_MAX;
+    // validate ids, gather sizes for the work split and the byte accounting
+    uint64_t max_n = 0, max_pal = 0;
+    uint32_t max_level = 0, max_pal_level = 0;
+    bool any_lit = false;
     long double sum_bytes = 0;
-    auto size_of = [&](uint32_t id) -> uint64_t { return c->genomes[id].desc.n; };
+    auto size_of = [&](uint32_t id) -> uint64_t { return c->genomes[id].desc.main.n; };
+    auto see = [&](uint32_t id) {
+        const GenomeRec &g = c->genomes[id];
+        max_n = std::max<uint64_t>(max_n, g.desc.main.n);
+        max_pal = std::max<uint64_t>(max_pal, g.desc.pal.n);
+        max_level = std::max(max_level, g.desc.main.level);
+        max_pal_level = std::max(max_pal_level, g.desc.pal.level);
+        any_lit = any_lit || !g.lit.empty();
+    };
     if (hp.mode == PAIRS_UPPER) {
         for (uint32_t i = 0; i < hp.n; i++) {
             if ((rc = check_built(c, i))) return rc;
-            max_n = std::max<uint64_t>(max_n, size_of(i));
-            if (size_of(i)) min_n = std::min<uint64_t>(min_n, size_of(i));
+            see(i);
         }
         // bytes of the requested range, row by row
         uint32_t i0 = 0, j0 = 1;
@@ -486,55 +727,55 @@ int run_pairs(gkd_ctx *c, const HostPairs &hp, uint64_t *inter, double *dist) {
         for (uint32_t i = 0; i < hp.na; i++) {
             if ((rc = check_built(c, hp.a[i]))) return rc;
             sq += size_of(hp.a[i]);
-            max_n = std::max<uint64_t>(max_n, size_of(hp.a[i]));
-            if (size_of(hp.a[i])) min_n = std::min<uint64_t>(min_n, size_of(hp.a[i]));
+            see(hp.a[i]);
         }
         for (uint32_t i = 0; i < hp.nb; i++) {
             if ((rc = check_built(c, hp.b[i]))) return rc;
             sr += size_of(hp.b[i]);
-            max_n = std::max<uint64_t>(max_n, size_of(hp.b[i]));
-            if (size_of(hp.b[i])) min_n = std::min<uint64_t>(min_n, size_of(hp.b[i]));
+            see(hp.b[i]);
         }
         sum_bytes = 8.0L * ((long double)sq * hp.nb + (long double)sr * hp.na);
     } else {
         for (uint64_t t = 0; t < hp.count; t++) {
             if ((rc = check_built(c, hp.a[t]))) return rc;
             if ((rc = check_built(c, hp.b[t]))) return rc;
-            uint64_t s = size_of(hp.a[t]) + size_of(hp.b[t]);
-            sum_bytes += 8.0L * s;
-            max_n = std::max<uint64_t>(max_n, std::max(size_of(hp.a[t]), size_of(hp.b[t])));
-            if (size_of(hp.a[t])) min_n = std::min<uint64_t>(min_n, size_of(hp.a[t]));
-            if (size_of(hp.b[t])) min_n = std::min<uint64_t>(min_n, size_of(hp.b[t]));
+            sum_bytes += 8.0L * (size_of(hp.a[t]) + size_of(hp.b[t]));
+            see(hp.a[t]);
+            see(hp.b[t]);
         }
     }
     c->m.intersect_bytes = (uint64_t)sum_bytes;
+    c->m.total_intersect_bytes += (uint64_t)sum_bytes;
+    c->m.total_pairs += hp.count;
     if (hp.count == 0) return GKD_OK;
+    c->m.intersect_kernel = c->low_bits == 32 ? 3u : 4u;
 
-    // palindrome side lists are tiny; the largest one decides which kernel intersects them
-    uint64_t max_pal = 0;
-    if (need_pal)
-        for (auto &g : c->genomes) max_pal = std::max<uint64_t>(max_pal, g.desc.n_pal);
-    const int algo = intersect_select(min_n == UINT64_MAX ? 0 : min_n, max_n, nuc ? 2 * c->k : 8 * c->k);
-    const bool small_main = c->cfg.segment_keys == 0 && max_n <= intersect_small_max_keys();
-    const bool small_pal = max_pal <= intersect_small_max_keys();
-    c->m.intersect_kernel = small_main ? 2u : (uint32_t)algo;
-
-    // merge-path segmenting: whole pairs when there are enough of them to fill the machine
-    const uint64_t max_l = std::max<uint64_t>(2 * max_n, 1);
-    const uint64_t target_items = (uint64_t)c->n_sms * intersect_items_per_sm(algo);
-    uint64_t seg = c->cfg.segment_keys;
-    if (seg == 0) {
-        if (hp.count >= target_items) seg = max_l;
+    // work split: a pair is walked in 32-bucket groups at the level of its larger set; an item is a run
+    // of groups of one pair.  Few pairs -> small items so every warp has work; many pairs -> eight items
+    // per pair, so the warps that share a pair read neighbouring parts of its two key streams.
+    auto make_plan = [&](uint64_t nmax, uint32_t lmax, bool one_item) {
+        IsectPlan p{};
+        p.low_bits = c->low_bits;
+        p.tmax = c->isect_tmax;
+        p.level_min = c->lvl_min;
+        uint32_t L = std::max(level_for((uint32_t)nmax, p.tmax), c->lvl_min);
+        L = std::min(L, lmax);
+        const uint64_t max_groups = ((1ull << L) + 31) >> 5;
+        uint64_t gpi;
+        if (one_item) gpi = max_groups;
+        else if (c->cfg.segment_keys) gpi = std::max<uint64_t>(1, c->cfg.segment_keys / (64ull * p.tmax));
         else {
-            uint64_t total_keys = (uint64_t)(sum_bytes / 8.0L);
-            // a segment must amortise its two global diagonal searches: ~5 CTA rounds, or ~70 warp steps
-            seg = std::max<uint64_t>(total_keys / target_items, algo ? 4096 : 16384);
-            seg = std::min<uint64_t>(seg, max_l);
+            const uint64_t warps = (uint64_t)c->n_sms * intersect_warps_per_sm(c->low_bits);
+            const long double total_groups = (long double)hp.count * max_groups;
+            gpi = (uint64_t)std::min<long double>(total_groups / (long double)(warps * 8), (long double)(max_groups / 8));
         }
-    }
-    seg = std::max<uint64_t>(seg, (uint64_t)intersect_min_segment(algo));
-    seg = std::min<uint64_t>(seg, 0xFFFF0000ull);
-    const uint32_t max_segs = (uint32_t)((max_l + seg - 1) / seg);
+        gpi = std::min<uint64_t>(std::max<uint64_t>(gpi, 1), max_groups);
+        p.groups_per_item = (uint32_t)gpi;
+        p.items_per_pair = (uint32_t)((max_groups + gpi - 1) / gpi);
+        return p;
+    };
+    const IsectPlan plan = make_plan(max_n, max_level, false);
+    const IsectPlan pal_plan = make_plan(max_pal, max_pal_level, true);
 
     // device id arrays
     PairSource src{};
@@ -572,40 +813,75 @@ int run_pairs(gkd_ctx *c, const HostPairs &hp, uint64_t *inter, double *dist) {
             if ((rc = ensure(c, c->pal_counts, cnt * 4))) return rc;
             CK(cudaMemsetAsync(c->pal_counts.p, 0, cnt * 4, c->stream));
         }
-        if (inter && (rc = ensure(c, c->d_inter, cnt * 8))) return rc;
-        if (dist && (rc = ensure(c, c->d_dist, cnt * 8))) return rc;
+        // with literal side lists the pairs are completed on the host, which needs the counts
+        const bool want_inter = out.inter || any_lit;
+        if (want_inter && (rc = ensure(c, c->d_inter, cnt * 8))) return rc;
+        if (out.dist && (rc = ensure(c, c->d_dist, cnt * 8))) return rc;
+        if (out.contain_a && (rc = ensure(c, c->d_ca, cnt * 8))) return rc;
+        if (out.contain_b && (rc = ensure(c, c->d_cb, cnt * 8))) return rc;
 
         CK(cudaEventRecord(c->ev[4], c->stream));
-        if (small_main)
-            CK(launch_intersect_small((const SetDesc *)c->d_sets.p, src, 0, (uint32_t *)c->counts.p, c->n_sms, c->stream));
-        else
-            CK(launch_intersect((const SetDesc *)c->d_sets.p, src, 0, (uint32_t)seg, max_segs, (uint32_t *)c->counts.p,
-                                (unsigned long long *)c->work_counter.p, c->n_sms, algo, c->stream));
+        nvtxRangePushA("gkd kernel 4: bucket-merge intersect");
+        CK(launch_intersect((const SetDesc *)c->d_sets.p, src, 0, plan, (uint32_t *)c->counts.p,
+                            (unsigned long long *)c->work_counter.p, c->n_sms, c->stream));
+        nvtxRangePop();
         CK(cudaEventRecord(c->ev[5], c->stream));
         c->m.launches++;
         c->m.intersect_launches++;
-        if (need_pal) {
-            if (small_pal)
-                CK(launch_intersect_small((const SetDesc *)c->d_sets.p, src, 1, (uint32_t *)c->pal_counts.p, c->n_sms,
-                                          c->stream));
-            else
-                CK(launch_intersect((const SetDesc *)c->d_sets.p, src, 1, (uint32_t)seg, max_segs,
-                                    (uint32_t *)c->pal_counts.p, (unsigned long long *)c->work_counter.p, c->n_sms,
-                                    algo, c->stream));
+        if (need_pal && max_pal) {
+            CK(launch_intersect((const SetDesc *)c->d_sets.p, src, 1, pal_plan, (uint32_t *)c->pal_counts.p,
+                                (unsigned long long *)c->work_counter.p, c->n_sms, c->stream));
             c->m.launches++;
         }
         CK(cudaEventRecord(c->ev[6], c->stream));
+        EpilogueOut eo{want_inter ? (uint64_t *)c->d_inter.p : nullptr, out.dist ? (double *)c->d_dist.p : nullptr,
+                       out.contain_a ? (double *)c->d_ca.p : nullptr, out.contain_b ? (double *)c->d_cb.p : nullptr};
+        nvtxRangePushA("gkd kernel 5: distance epilogue");
         CK(launch_epilogue((const SetDesc *)c->d_sets.p, src, (const uint32_t *)c->counts.p,
-                           need_pal ? (const uint32_t *)c->pal_counts.p : nullptr, both ? 1 : 0,
-                           inter ? (uint64_t *)c->d_inter.p : nullptr, dist ? (double *)c->d_dist.p : nullptr, c->stream));
+                           need_pal ? (const uint32_t *)c->pal_counts.p : nullptr, both ? 1 : 0, eo, c->stream));
+        nvtxRangePop();
         c->m.launches++;
         CK(cudaEventRecord(c->ev[7], c->stream));
-        if (inter) CK(cudaMemcpyAsync(inter + done, c->d_inter.p, cnt * 8, cudaMemcpyDefault, c->stream));
-        if (dist) CK(cudaMemcpyAsync(dist + done, c->d_dist.p, cnt * 8, cudaMemcpyDefault, c->stream));
+        std::vector<uint64_t> tmp_inter;
+        uint64_t *h_inter = out.inter ? out.inter + done : nullptr;
+        if (any_lit && !h_inter) {
+            tmp_inter.resize(cnt);
+            h_inter = tmp_inter.data();
+        }
+        uint64_t d2h = 0;
+        const struct {
+            void *dst;
+            const void *src;
+        } copies[4] = {{h_inter, c->d_inter.p}, {out.dist ? out.dist + done : nullptr, c->d_dist.p},
+                       {out.contain_a ? out.contain_a + done : nullptr, c->d_ca.p},
+                       {out.contain_b ? out.contain_b + done : nullptr, c->d_cb.p}};
+        for (const auto &cp : copies) {
+            if (!cp.dst) continue;
+            CK(cudaMemcpyAsync(cp.dst, cp.src, cnt * 8, cudaMemcpyDefault, c->stream));
+            d2h += cnt * 8;
+        }
         CK(cudaStreamSynchronize(c->stream));
-        c->m.d2h_bytes += (inter ? cnt * 8 : 0) + (dist ? cnt * 8 : 0);
-        c->m.intersect_ms += elapsed(c->ev[4], c->ev[5]);
+        c->m.d2h_bytes += d2h;
+        const double ims = elapsed(c->ev[4], c->ev[5]);
+        c->m.intersect_ms += ims;
+        c->m.total_intersect_ms += ims;
         c->m.epilogue_ms += elapsed(c->ev[6], c->ev[7]);
+        if (any_lit) {
+            // GKD_AMBIG_LITERAL: add the literal k-mers both sets share and redo the formula with the
+            // full sizes (outputs must be host memory in this mode)
+            for (uint64_t t = 0; t < cnt; t++) {
+                uint32_t a, b;
+                host_pair_ids(hp, done + t, a, b);
+                const GenomeRec &ga = c->genomes[a], &gb = c->genomes[b];
+                if (ga.lit.empty() && gb.lit.empty()) continue;
+                const uint64_t I = h_inter[t] + literal_intersection(ga.lit, gb.lit);
+                const uint64_t sa = both_size(c, ga), sb = both_size(c, gb);
+                if (out.inter) out.inter[done + t] = I;
+                if (out.dist) out.dist[done + t] = host_distance(I, sa, sb);
+                if (out.contain_a) out.contain_a[done + t] = sa ? (double)I / (double)sa : 0.0;
+                if (out.contain_b) out.contain_b[done + t] = sb ? (double)I / (double)sb : 0.0;
+            }
+        }
     }
     return GKD_OK;
 }
@@ -633,6 +909,10 @@ int gkd_create(gkd_ctx **out, const gkd_config *cfg) {
         return fail(nullptr, GKD_EINVAL, "kmer size %d is outside the exact-key range 1..%d of this alphabet", k, kmax);
     if (cfg->strand_mode != GKD_STRAND_BOTH && cfg->strand_mode != GKD_STRAND_CANONICAL)
         return fail(nullptr, GKD_EINVAL, "unknown strand mode %d", cfg->strand_mode);
+    if (cfg->ambig_policy != GKD_AMBIG_SKIP && cfg->ambig_policy != GKD_AMBIG_LITERAL)
+        return fail(nullptr, GKD_EINVAL, "unknown ambiguity policy %d", cfg->ambig_policy);
+    if (cfg->ambig_policy == GKD_AMBIG_LITERAL && cfg->alphabet != GKD_PROT && cfg->strand_mode != GKD_STRAND_BOTH)
+        return fail(nullptr, GKD_EINVAL, "literal ambiguous k-mers are defined for the both-strand sets only");
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
     if (e != cudaSuccess || ndev == 0) {
@@ -653,6 +933,13 @@ int gkd_create(gkd_ctx **out, const gkd_config *cfg) {
     c->cfg.k = k;
     if (c->cfg.workspace_bytes == 0) c->cfg.workspace_bytes = DEFAULT_WORKSPACE;
     c->n_sms = prop.multiProcessorCount;
+    c->key_bits = cfg->alphabet == GKD_PROT ? 8 * k : 2 * k;
+    c->low_bits = low_bits_for(c->key_bits);
+    c->lvl_min = level_min(c->key_bits, c->low_bits);
+    c->mix = make_mix(c->key_bits);
+    c->isect_tmax = intersect_default_tmax(c->low_bits);
+    c->table_tmax = c->isect_tmax;
+    if (const char *t = getenv("GKD_TABLE_TMAX")) c->table_tmax = (uint32_t)std::max(1, atoi(t));
 #define CK_CREATE(call)                                                                        \
     do {                                                                                       \
         cudaError_t e__ = (call);                                                              \
@@ -674,9 +961,29 @@ int gkd_create(gkd_ctx **out, const gkd_config *cfg) {
         CK_CREATE(cudaMalloc((void **)&c->stage_dev[i], STAGE_BYTES + 256));
     }
     for (auto &ev : c->ev) CK_CREATE(cudaEventCreate(&ev));
+    // function attributes are per device: every context sets them for its own device
     CK_CREATE(intersect_configure());
+    CK_CREATE(sort_configure());
 #undef CK_CREATE
     *out = c;
+    return GKD_OK;
+}
+
+static void release_arenas_from(gkd_ctx *c, size_t first_dropped) {
+    for (size_t i = first_dropped; i < c->arenas.size(); i++)
+        if (c->arenas[i].owned) c->free_arenas.push_back({c->arenas[i].base, c->arenas[i].capacity});
+    c->arenas.resize(first_dropped);
+}
+
+static int trim_free_arenas(gkd_ctx *c, size_t keep) {
+    // keep at most a handful of spare arenas; release the smallest ones beyond that
+    while (c->free_arenas.size() > keep) {
+        size_t small = 0;
+        for (size_t i = 1; i < c->free_arenas.size(); i++)
+            if (c->free_arenas[i].second < c->free_arenas[small].second) small = i;
+        CK(cudaFreeAsync(c->free_arenas[small].first, c->stream));
+        c->free_arenas.erase(c->free_arenas.begin() + small);
+    }
     return GKD_OK;
 }
 
@@ -684,19 +991,12 @@ int gkd_reset(gkd_ctx *c) {
     CHECK_CTX(c);
     CK(cudaSetDevice(c->cfg.device));
     CK(cudaStreamSynchronize(c->stream));
-    for (auto &a : c->set_arenas) c->free_arenas.push_back(a);
-    c->set_arenas.clear();
-    c->arena_first_id.clear();
-    // keep at most a handful of spare arenas; release the smallest ones beyond that
-    while (c->free_arenas.size() > 16) {
-        size_t small = 0;
-        for (size_t i = 1; i < c->free_arenas.size(); i++)
-            if (c->free_arenas[i].second < c->free_arenas[small].second) small = i;
-        CK(cudaFreeAsync(c->free_arenas[small].first, c->stream));
-        c->free_arenas.erase(c->free_arenas.begin() + small);
-    }
+    release_arenas_from(c, 0);
+    int rc = trim_free_arenas(c, 16);
+    if (rc) return rc;
     for (auto &s : c->slabs) s.used = 0;
     c->genomes.clear();
+    c->lit_dict.clear();
     c->built_upto = 0;
     c->sets_dirty = true;
     uint64_t launches = c->m.launches, il = c->m.intersect_launches;
@@ -711,12 +1011,12 @@ int gkd_truncate(gkd_ctx *c, uint32_t n_keep) {
     if (n_keep >= c->genomes.size()) return GKD_OK;
     CK(cudaSetDevice(c->cfg.device));
     CK(cudaStreamSynchronize(c->stream));
-    // arenas are created in id order, one per build/import batch: recycle those that hold only dropped sets
-    while (!c->set_arenas.empty() && c->arena_first_id.back() >= n_keep) {
-        c->free_arenas.push_back(c->set_arenas.back());
-        c->set_arenas.pop_back();
-        c->arena_first_id.pop_back();
-    }
+    // arenas are created in id order, one per build/import/adopt batch: recycle those that hold only dropped sets
+    size_t keep = c->arenas.size();
+    while (keep > 0 && c->arenas[keep - 1].first_id >= n_keep) keep--;
+    release_arenas_from(c, keep);
+    int rc = trim_free_arenas(c, 16);
+    if (rc) return rc;
     c->genomes.resize(n_keep);
     if (c->built_upto > n_keep) c->built_upto = n_keep;
     c->sets_dirty = true;
@@ -727,12 +1027,13 @@ int gkd_destroy(gkd_ctx *c) {
     if (!c) return GKD_EINVAL;
     cudaSetDevice(c->cfg.device);
     cudaStreamSynchronize(c->stream);
-    for (auto &a : c->set_arenas) cudaFreeAsync(a.first, c->stream);
+    for (auto &a : c->arenas)
+        if (a.owned) cudaFreeAsync(a.base, c->stream);
     for (auto &a : c->free_arenas) cudaFreeAsync(a.first, c->stream);
     for (auto &s : c->slabs) cudaFreeAsync(s.base, c->stream);
     DevBuf *bufs[] = {&c->keys_a, &c->keys_b, &c->tile_hist, &c->tile_uniq, &c->genome_counts, &c->batch_genomes,
-                      &c->uniq_dst, &c->d_sets, &c->counts, &c->pal_counts, &c->d_inter, &c->d_dist, &c->ids_a,
-                      &c->ids_b, &c->work_counter};
+                      &c->set_build, &c->d_sets, &c->counts, &c->pal_counts, &c->d_inter, &c->d_dist, &c->d_ca,
+                      &c->d_cb, &c->ids_a, &c->ids_b, &c->work_counter};
     for (DevBuf *b : bufs)
         if (b->p) cudaFreeAsync(b->p, c->stream);
     cudaStreamSynchronize(c->stream);
@@ -753,6 +1054,7 @@ int gkd_add_sequences(gkd_ctx *c, const char *const *contigs, const uint64_t *le
     CHECK_CTX(c);
     if (n_contigs && (!contigs || !lens)) return fail(c, GKD_EINVAL, "gkd_add_sequences: null contig array");
     CK(cudaSetDevice(c->cfg.device));
+    ABI_GUARD_BEGIN
     std::vector<Part> parts;
     parts.reserve(n_contigs);
     for (uint32_t i = 0; i < n_contigs; i++) {
@@ -760,12 +1062,14 @@ int gkd_add_sequences(gkd_ctx *c, const char *const *contigs, const uint64_t *le
         parts.push_back(Part{contigs[i], lens[i], true});
     }
     return add_genome(c, parts, "", "", out_id);
+    ABI_GUARD_END(c)
 }
 
 int gkd_add_fasta_file(gkd_ctx *c, const char *path, int per_record, uint32_t *first_id, uint32_t *n_added) {
     CHECK_CTX(c);
     if (!path) return fail(c, GKD_EINVAL, "gkd_add_fasta_file: null path");
     CK(cudaSetDevice(c->cfg.device));
+    ABI_GUARD_BEGIN
     std::vector<char> storage;
     std::vector<FastaRecord> recs;
     std::string err;
@@ -798,10 +1102,11 @@ int gkd_add_fasta_file(gkd_ctx *c, const char *path, int per_record, uint32_t *f
         if (rc) return rc;
         added = 1;
     }
-    // the staged pieces reference `storage`; they were consumed by memcpy before add_genome returned
+    // the staged pieces reference `storage` (pageable): they were consumed by memcpy before add_genome returned
     if (first_id) *first_id = first;
     if (n_added) *n_added = added;
     return GKD_OK;
+    ABI_GUARD_END(c)
 }
 
 const char *gkd_label(const gkd_ctx *c, uint32_t id) { return (c && id < c->genomes.size()) ? c->genomes[id].label.c_str() : ""; }
@@ -811,6 +1116,7 @@ uint32_t gkd_count(const gkd_ctx *c) { return c ? (uint32_t)c->genomes.size() : 
 int gkd_build_sets(gkd_ctx *c) {
     CHECK_CTX(c);
     CK(cudaSetDevice(c->cfg.device));
+    ABI_GUARD_BEGIN
     const uint32_t n = (uint32_t)c->genomes.size();
     // skip sets that were imported ready-made
     while (c->built_upto < n) {
@@ -833,17 +1139,19 @@ int gkd_build_sets(gkd_ctx *c) {
         if (rc) return rc;
         c->built_upto = last;
     }
+    // pinned / device input text of gkd_add_sequences may be released by the caller from here on
+    CK(cudaStreamSynchronize(c->stream));
     return upload_sets(c);
+    ABI_GUARD_END(c)
 }
 
 int gkd_set_size(const gkd_ctx *c, uint32_t id, uint64_t *n_both, uint64_t *n_canonical, uint64_t *n_palindromic) {
     if (!c) return GKD_EINVAL;
     if (id >= c->genomes.size() || !c->genomes[id].built) return GKD_ESTATE;
-    const SetDesc &d = c->genomes[id].desc;
-    const bool both = c->cfg.alphabet != GKD_PROT && c->cfg.strand_mode == GKD_STRAND_BOTH;
-    if (n_both) *n_both = both ? 2ull * d.n - d.n_pal : d.n;
-    if (n_canonical) *n_canonical = d.n;
-    if (n_palindromic) *n_palindromic = d.n_pal;
+    const GenomeRec &g = c->genomes[id];
+    if (n_both) *n_both = both_size(c, g);
+    if (n_canonical) *n_canonical = g.desc.main.n;
+    if (n_palindromic) *n_palindromic = g.desc.pal.n;
     return GKD_OK;
 }
 
@@ -852,72 +1160,57 @@ int gkd_export_set(gkd_ctx *c, uint32_t id, uint64_t *keys, uint64_t cap, uint64
     int rc = check_built(c, id);
     if (rc) return rc;
     const SetDesc &d = c->genomes[id].desc;
-    if (n) *n = d.n;
-    if (keys) {
-        if (cap < d.n) return fail(c, GKD_EINVAL, "export buffer holds %llu keys, set has %u", (unsigned long long)cap, d.n);
-        CK(cudaSetDevice(c->cfg.device));
-        if (d.n) CK(cudaMemcpyAsync(keys, d.keys, (uint64_t)d.n * 8, cudaMemcpyDefault, c->stream));
-        CK(cudaStreamSynchronize(c->stream));
-        c->m.d2h_bytes += (uint64_t)d.n * 8;
-    }
+    if (n) *n = d.main.n;
+    if (!keys) return GKD_OK;
+    if (cap < d.main.n) return fail(c, GKD_EINVAL, "export buffer holds %llu keys, set has %u", (unsigned long long)cap, d.main.n);
+    if (d.main.n == 0) return GKD_OK;
+    CK(cudaSetDevice(c->cfg.device));
+    ABI_GUARD_BEGIN
+    // un-mix into the sort workspace, sort ascending by key, copy out
+    std::vector<BatchGenome> bg(1);
+    bg[0] = BatchGenome{nullptr, nullptr, 0, 0, d.main.n, 0, (d.main.n + SORT_TILE - 1) / SORT_TILE};
+    SortPlan plan{};
+    if ((rc = plan_batch(c, bg, plan, d.main.n, bg[0].n_tiles))) return rc;
+    CK(launch_unmix_set(d.main, c->mix, c->low_bits, plan.keys_a, c->stream));
+    uint64_t *sorted = nullptr;
+    uint32_t passes = 0;
+    CK(launch_sort((const BatchGenome *)c->batch_genomes.p, plan, &sorted, &passes, c->stream));
+    c->m.launches += 1 + 3ull * passes;
+    CK(cudaMemcpyAsync(keys, sorted, (uint64_t)d.main.n * 8, cudaMemcpyDefault, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    c->m.d2h_bytes += (uint64_t)d.main.n * 8;
     return GKD_OK;
-}
-
-int gkd_set_device_ptr(const gkd_ctx *c, uint32_t id, const uint64_t **keys, uint64_t *n) {
-    if (!c) return GKD_EINVAL;
-    if (id >= c->genomes.size() || !c->genomes[id].built) return GKD_ESTATE;
-    if (keys) *keys = c->genomes[id].desc.keys;
-    if (n) *n = c->genomes[id].desc.n;
-    return GKD_OK;
+    ABI_GUARD_END(c)
 }
 
 int gkd_import_sets(gkd_ctx *c, const uint64_t *keys, const uint64_t *offsets, uint32_t n_sets, uint32_t *first_id) {
     CHECK_CTX(c);
-    if (n_sets == 0) {
-        if (first_id) *first_id = (uint32_t)c->genomes.size();
-        return GKD_OK;
-    }
+    if (first_id) *first_id = (uint32_t)c->genomes.size();
+    if (n_sets == 0) return GKD_OK;
     if (!offsets) return fail(c, GKD_EINVAL, "gkd_import_sets: null offsets");
-    const uint64_t total = offsets[n_sets];
+    const uint64_t total = offsets[n_sets] - offsets[0];
     if (total && !keys) return fail(c, GKD_EINVAL, "gkd_import_sets: null keys");
-    CK(cudaSetDevice(c->cfg.device));
-    // treat the arrays as an already-sorted batch and run the unique/compact pass: that re-derives
-    // the palindrome lists and drops any duplicate the caller left in
-    const uint32_t id0 = (uint32_t)c->genomes.size();
-    std::vector<BatchGenome> bg(n_sets);
-    std::vector<uint32_t> ids(n_sets);
-    uint32_t tiles = 0;
-    for (uint32_t i = 0; i < n_sets; i++) {
+    for (uint32_t i = 0; i < n_sets; i++)
         if (offsets[i + 1] < offsets[i] || offsets[i + 1] - offsets[i] >= 0xFFFF0000ull)
             return fail(c, GKD_EINVAL, "gkd_import_sets: bad offsets at set %u", i);
-        bg[i].codes = nullptr;
-        bg[i].mask = nullptr;
-        bg[i].raw_off = offsets[i];
-        bg[i].n_pos = 0;
-        bg[i].n_slots = (uint32_t)(offsets[i + 1] - offsets[i]);
-        bg[i].tile_first = tiles;
-        bg[i].n_tiles = (bg[i].n_slots + SORT_TILE - 1) / SORT_TILE;
-        tiles += bg[i].n_tiles;
-        ids[i] = id0 + i;
-    }
+    CK(cudaSetDevice(c->cfg.device));
+    ABI_GUARD_BEGIN
     const bool on_device = total && classify(keys) == MEM_DEVICE;
-    SortPlan plan{};
-    int rc = plan_batch(c, bg, plan, on_device ? 16 : std::max<uint64_t>(total, 16), tiles);
-    if (rc) return rc;
-    const uint64_t *sorted = keys;
-    if (!on_device) {
-        if (total) CK(cudaMemcpyAsync(plan.keys_a, keys, total * 8, cudaMemcpyHostToDevice, c->stream));
-        sorted = plan.keys_a;
-        c->m.h2d_bytes += total * 8;
+    // batches under the workspace cap, like gkd_build_sets
+    const uint64_t cap_keys = std::max<uint64_t>(c->cfg.workspace_bytes / 16, SORT_TILE);
+    const uint32_t id0 = (uint32_t)c->genomes.size();
+    for (uint32_t i0 = 0; i0 < n_sets;) {
+        uint32_t i1 = i0 + 1;
+        while (i1 < n_sets && offsets[i1 + 1] - offsets[i0] <= cap_keys) i1++;
+        int rc = import_device_batch(c, keys, offsets, i0, i1, on_device);
+        if (rc) {
+            gkd_truncate(c, id0);
+            return rc;
+        }
+        i0 = i1;
     }
-    for (uint32_t i = 0; i < n_sets; i++) c->genomes.push_back(GenomeRec());
-    rc = finish_batch(c, bg, ids, plan, sorted);
-    if (rc) {
-        c->genomes.resize(id0);
-        return rc;
-    }
-    if (first_id) *first_id = id0;
     return GKD_OK;
+    ABI_GUARD_END(c)
 }
 
 int gkd_import_set(gkd_ctx *c, const uint64_t *keys, uint64_t n, uint32_t *out_id) {
@@ -925,8 +1218,76 @@ int gkd_import_set(gkd_ctx *c, const uint64_t *keys, uint64_t n, uint32_t *out_i
     return gkd_import_sets(c, keys, offsets, 1, out_id);
 }
 
+// ---- set exchange ---------------------------------------------------------------------------------------
+uint32_t gkd_arena_count(const gkd_ctx *c) { return c ? (uint32_t)c->arenas.size() : 0; }
+
+int gkd_arena_info(const gkd_ctx *c, uint32_t arena, uint32_t *first_id, uint32_t *n_sets, const void **base, uint64_t *bytes) {
+    if (!c || arena >= c->arenas.size()) return GKD_EINVAL;
+    const Arena &a = c->arenas[arena];
+    if (first_id) *first_id = a.first_id;
+    if (n_sets) *n_sets = a.n_sets;
+    if (base) *base = a.base;
+    if (bytes) *bytes = a.bytes;
+    return GKD_OK;
+}
+
+int gkd_describe_sets(const gkd_ctx *cc, uint32_t first_id, uint32_t n_sets, gkd_packed_set *table) {
+    gkd_ctx *c = const_cast<gkd_ctx *>(cc);
+    if (!c) return GKD_EINVAL;
+    if (n_sets == 0) return GKD_OK;
+    if (!table) return fail(c, GKD_EINVAL, "gkd_describe_sets: null table");
+    if ((uint64_t)first_id + n_sets > c->genomes.size()) return fail(c, GKD_EINVAL, "gkd_describe_sets: ids out of range");
+    const int arena = c->genomes[first_id].arena;
+    for (uint32_t i = 0; i < n_sets; i++) {
+        const GenomeRec &g = c->genomes[first_id + i];
+        if (!g.built) return fail(c, GKD_ESTATE, "set %u has not been built", first_id + i);
+        if (g.arena != arena) return fail(c, GKD_EINVAL, "sets %u..%u span more than one arena", first_id, first_id + n_sets - 1);
+        if (!g.lit.empty()) return fail(c, GKD_EINVAL, "set %u has literal ambiguous k-mers, which live on the host and are not exchanged", first_id + i);
+        table[i] = g.packed;
+    }
+    return GKD_OK;
+}
+
+int gkd_adopt_sets(gkd_ctx *c, const void *base, uint64_t bytes, const gkd_packed_set *table, uint32_t n_sets, uint32_t *first_id) {
+    CHECK_CTX(c);
+    if (first_id) *first_id = (uint32_t)c->genomes.size();
+    if (n_sets == 0) return GKD_OK;
+    if (!base || !table) return fail(c, GKD_EINVAL, "gkd_adopt_sets: null argument");
+    if (((uintptr_t)base & 15) != 0) return fail(c, GKD_EINVAL, "gkd_adopt_sets: base must be 16-byte aligned");
+    if (classify(base) != MEM_DEVICE) return fail(c, GKD_EINVAL, "gkd_adopt_sets: base must be device memory");
+    const uint64_t lsz = c->low_bits / 8;
+    const bool pal = has_pal_lists(c);
+    ABI_GUARD_BEGIN
+    for (uint32_t i = 0; i < n_sets; i++) {
+        const gkd_packed_set &p = table[i];
+        auto piece_ok = [&](uint64_t off, uint64_t len) { return (off & 15) == 0 && off <= bytes && len <= bytes - off; };
+        bool ok = p.level >= c->lvl_min && p.level <= level_cap(c->key_bits) &&
+                  piece_ok(p.offs_off, ((1ull << p.level) + 1) * 4) && piece_ok(p.lows_off, align16((uint64_t)p.n * lsz));
+        if (ok && pal)
+            ok = p.pal_level >= c->lvl_min && p.pal_level <= level_cap(c->key_bits) && p.pal_lows_off != 0 &&
+                 piece_ok(p.pal_offs_off, ((1ull << p.pal_level) + 1) * 4) &&
+                 piece_ok(p.pal_lows_off, align16((uint64_t)p.n_pal * lsz));
+        if (ok && !pal) ok = p.n_pal == 0;
+        if (!ok) return fail(c, GKD_EINVAL, "gkd_adopt_sets: descriptor %u does not fit the buffer or this context (k, alphabet)", i);
+    }
+    const uint32_t id0 = (uint32_t)c->genomes.size();
+    c->arenas.push_back(Arena{(char *)const_cast<void *>(base), bytes, bytes, id0, n_sets, false});
+    for (uint32_t i = 0; i < n_sets; i++) {
+        GenomeRec g;
+        g.packed = table[i];
+        if (!pal) g.packed.pal_offs_off = g.packed.pal_lows_off = 0;
+        g.arena = (int)c->arenas.size() - 1;
+        set_desc_from_packed(g, (const char *)base);
+        g.built = true;
+        c->genomes.push_back(std::move(g));
+    }
+    c->sets_dirty = true;
+    return GKD_OK;
+    ABI_GUARD_END(c)
+}
+
 // .kset layout (little-endian): "GKDKSET1", u32 k, u32 alphabet, u32 n_sets, u32 0; then per set:
-// u64 n_keys, u32 label_len, u32 comment_len, label bytes, comment bytes, n_keys x u64 sorted keys.
+// u64 n_keys, u32 label_len, u32 comment_len, label bytes, comment bytes, n_keys x u64 keys ascending.
 int gkd_save_sets(gkd_ctx *c, const char *path) {
     CHECK_CTX(c);
     if (!path) return fail(c, GKD_EINVAL, "gkd_save_sets: null path");
@@ -934,7 +1295,9 @@ int gkd_save_sets(gkd_ctx *c, const char *path) {
     for (uint32_t i = 0; i < c->genomes.size(); i++) {
         int rc = check_built(c, i);
         if (rc) return rc;
+        if (!c->genomes[i].lit.empty()) return fail(c, GKD_EINVAL, "set %u has literal ambiguous k-mers, which the .kset cache cannot hold", i);
     }
+    ABI_GUARD_BEGIN
     FILE *f = fopen(path, "wb");
     if (!f) return fail(c, GKD_EIO, "Cannot open %s for writing.", path);
     uint32_t hdr[4] = {(uint32_t)c->k, (uint32_t)c->cfg.alphabet, (uint32_t)c->genomes.size(), 0};
@@ -942,17 +1305,13 @@ int gkd_save_sets(gkd_ctx *c, const char *path) {
     std::vector<uint64_t> host;
     for (uint32_t i = 0; ok && i < c->genomes.size(); i++) {
         const GenomeRec &g = c->genomes[i];
-        uint64_t n = g.desc.n;
+        uint64_t n = g.desc.main.n;
         uint32_t ll[2] = {(uint32_t)g.label.size(), (uint32_t)g.comment.size()};
         host.resize(n);
-        if (n) {
-            cudaError_t e = cudaMemcpyAsync(host.data(), g.desc.keys, n * 8, cudaMemcpyDeviceToHost, c->stream);
-            if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
-            if (e != cudaSuccess) {
-                fclose(f);
-                c->poisoned = true;
-                return fail(c, GKD_ECUDA, "gkd_save_sets: %s", cudaGetErrorString(e));
-            }
+        int rc = gkd_export_set(c, i, host.data(), n, nullptr);
+        if (rc) {
+            fclose(f);
+            return rc;
         }
         ok = fwrite(&n, 8, 1, f) == 1 && fwrite(ll, 4, 2, f) == 2 &&
              fwrite(g.label.data(), 1, ll[0], f) == ll[0] && fwrite(g.comment.data(), 1, ll[1], f) == ll[1] &&
@@ -960,32 +1319,44 @@ int gkd_save_sets(gkd_ctx *c, const char *path) {
     }
     ok = (fclose(f) == 0) && ok;
     return ok ? GKD_OK : fail(c, GKD_EIO, "Write error on %s.", path);
+    ABI_GUARD_END(c)
 }
 
 int gkd_load_sets(gkd_ctx *c, const char *path, uint32_t *first_id, uint32_t *n_loaded) {
     CHECK_CTX(c);
     if (!path) return fail(c, GKD_EINVAL, "gkd_load_sets: null path");
+    ABI_GUARD_BEGIN
     FILE *f = fopen(path, "rb");
     if (!f) return fail(c, GKD_EIO, "Input file %s is not found or unreadable.", path);
+    struct Closer {
+        FILE *f;
+        ~Closer() { fclose(f); }
+    } closer{f};
     char magic[8];
     uint32_t hdr[4];
-    if (fread(magic, 1, 8, f) != 8 || memcmp(magic, "GKDKSET1", 8) != 0 || fread(hdr, 4, 4, f) != 4) {
-        fclose(f);
+    if (fread(magic, 1, 8, f) != 8 || memcmp(magic, "GKDKSET1", 8) != 0 || fread(hdr, 4, 4, f) != 4)
         return fail(c, GKD_EIO, "%s is not a .kset file.", path);
-    }
-    if ((int)hdr[0] != c->k || (int)hdr[1] != c->cfg.alphabet) {
-        fclose(f);
+    if ((int)hdr[0] != c->k || (int)hdr[1] != c->cfg.alphabet)
         return fail(c, GKD_EINVAL, "%s holds k=%u alphabet=%u sets; this context is k=%d alphabet=%d", path, hdr[0], hdr[1],
                     c->k, c->cfg.alphabet);
-    }
+    // the file is untrusted: every count is bounded by the bytes that are actually left in it
+    long here = ftell(f);
+    if (here < 0 || fseek(f, 0, SEEK_END) != 0) return fail(c, GKD_EIO, "%s is not seekable.", path);
+    const uint64_t file_size = (uint64_t)ftell(f);
+    fseek(f, here, SEEK_SET);
+    uint64_t left = file_size - (uint64_t)here;
     const uint32_t n = hdr[2];
+    if ((uint64_t)n * 16 > left) return fail(c, GKD_EIO, "%s is truncated or corrupt.", path);
     std::vector<uint64_t> keys, offsets(1, 0);
     std::vector<std::string> labels(n), comments(n);
     bool ok = true;
     for (uint32_t i = 0; ok && i < n; i++) {
         uint64_t nk;
         uint32_t ll[2];
-        ok = fread(&nk, 8, 1, f) == 1 && fread(ll, 4, 2, f) == 2 && nk < 0xFFFF0000ull && ll[0] < (1u << 20) && ll[1] < (1u << 20);
+        ok = fread(&nk, 8, 1, f) == 1 && fread(ll, 4, 2, f) == 2;
+        if (!ok) break;
+        left -= 16;
+        ok = nk < 0xFFFF0000ull && (uint64_t)ll[0] + ll[1] <= left && nk <= (left - ll[0] - ll[1]) / 8;
         if (!ok) break;
         labels[i].resize(ll[0]);
         comments[i].resize(ll[1]);
@@ -994,9 +1365,9 @@ int gkd_load_sets(gkd_ctx *c, const char *path, uint32_t *first_id, uint32_t *n_
         size_t at = keys.size();
         keys.resize(at + nk);
         ok = fread(keys.data() + at, 8, nk, f) == nk;
+        left -= (uint64_t)ll[0] + ll[1] + nk * 8;
         offsets.push_back(keys.size());
     }
-    fclose(f);
     if (!ok) return fail(c, GKD_EIO, "%s is truncated or corrupt.", path);
     uint32_t first = 0;
     int rc = gkd_import_sets(c, keys.data(), offsets.data(), n, &first);
@@ -1008,42 +1379,68 @@ int gkd_load_sets(gkd_ctx *c, const char *path, uint32_t *first_id, uint32_t *n_
     if (first_id) *first_id = first;
     if (n_loaded) *n_loaded = n;
     return GKD_OK;
+    ABI_GUARD_END(c)
 }
 
-int gkd_all_vs_all(gkd_ctx *c, uint64_t *inter, double *dist) {
-    CHECK_CTX(c);
-    CK(cudaSetDevice(c->cfg.device));
-    uint32_t n = (uint32_t)c->genomes.size();
-    HostPairs hp{PAIRS_UPPER, n, 0, n < 2 ? 0 : (uint64_t)n * (n - 1) / 2, nullptr, nullptr, 0, 0};
-    return run_pairs(c, hp, inter, dist);
+// ---- distances --------------------------------------------------------------------------------------------
+static int lit_outputs_ok(gkd_ctx *c, const gkd_outputs &o) {
+    // literal side lists are completed on the host, so the outputs must be host memory in that mode
+    if (c->cfg.ambig_policy != GKD_AMBIG_LITERAL) return GKD_OK;
+    const void *ps[4] = {o.inter, o.dist, o.contain_a, o.contain_b};
+    for (const void *p : ps)
+        if (p && classify(p) == MEM_DEVICE) return fail(c, GKD_EINVAL, "GKD_AMBIG_LITERAL needs host output buffers");
+    return GKD_OK;
 }
 
-int gkd_all_vs_all_range(gkd_ctx *c, uint32_t n, uint64_t first, uint64_t count, uint64_t *inter, double *dist) {
+int gkd_all_vs_all_range_ex(gkd_ctx *c, uint32_t n, uint64_t first, uint64_t count, const gkd_outputs *out) {
     CHECK_CTX(c);
+    if (!out) return fail(c, GKD_EINVAL, "null outputs");
     CK(cudaSetDevice(c->cfg.device));
     if (n > c->genomes.size()) return fail(c, GKD_EINVAL, "range over %u sets but only %zu exist", n, c->genomes.size());
     uint64_t total = n < 2 ? 0 : (uint64_t)n * (n - 1) / 2;
     if (first > total || count > total - first) return fail(c, GKD_EINVAL, "pair range [%llu, +%llu) outside 0..%llu", (unsigned long long)first, (unsigned long long)count, (unsigned long long)total);
+    int rc = lit_outputs_ok(c, *out);
+    if (rc) return rc;
+    ABI_GUARD_BEGIN
     HostPairs hp{PAIRS_UPPER, n, first, count, nullptr, nullptr, 0, 0};
-    return run_pairs(c, hp, inter, dist);
+    return run_pairs(c, hp, *out);
+    ABI_GUARD_END(c)
 }
 
-int gkd_query_vs_ref(gkd_ctx *c, const uint32_t *q, uint32_t nq, const uint32_t *r, uint32_t nr, uint64_t *inter, double *dist) {
+int gkd_all_vs_all_range(gkd_ctx *c, uint32_t n, uint64_t first, uint64_t count, uint64_t *inter, double *dist) {
+    gkd_outputs o{inter, dist, nullptr, nullptr};
+    return gkd_all_vs_all_range_ex(c, n, first, count, &o);
+}
+
+int gkd_all_vs_all(gkd_ctx *c, uint64_t *inter, double *dist) {
     CHECK_CTX(c);
+    uint32_t n = (uint32_t)c->genomes.size();
+    return gkd_all_vs_all_range(c, n, 0, n < 2 ? 0 : (uint64_t)n * (n - 1) / 2, inter, dist);
+}
+
+int gkd_query_vs_ref_ex(gkd_ctx *c, const uint32_t *q, uint32_t nq, const uint32_t *r, uint32_t nr, const gkd_outputs *out) {
+    CHECK_CTX(c);
+    if (!out) return fail(c, GKD_EINVAL, "null outputs");
     CK(cudaSetDevice(c->cfg.device));
     if ((nq && !q) || (nr && !r)) return fail(c, GKD_EINVAL, "gkd_query_vs_ref: null id array");
+    int rc = lit_outputs_ok(c, *out);
+    if (rc) return rc;
     // large blocks are split by query rows so each launch stays under PAIR_CHUNK pairs
     if (nq == 0 || nr == 0) {
         c->m.pairs = 0;
         return GKD_OK;
     }
+    ABI_GUARD_BEGIN
     uint32_t rows_per = (uint32_t)std::max<uint64_t>(1, PAIR_CHUNK / nr);
     uint64_t pairs = 0, bytes = 0;
     double ims = 0, ems = 0;
     for (uint32_t q0 = 0; q0 < nq; q0 += rows_per) {
         uint32_t rows = std::min(rows_per, nq - q0);
         HostPairs hp{PAIRS_RECT, nr, 0, (uint64_t)rows * nr, q + q0, r, rows, nr};
-        int rc = run_pairs(c, hp, inter ? inter + (uint64_t)q0 * nr : nullptr, dist ? dist + (uint64_t)q0 * nr : nullptr);
+        const uint64_t at = (uint64_t)q0 * nr;
+        gkd_outputs o{out->inter ? out->inter + at : nullptr, out->dist ? out->dist + at : nullptr,
+                      out->contain_a ? out->contain_a + at : nullptr, out->contain_b ? out->contain_b + at : nullptr};
+        rc = run_pairs(c, hp, o);
         if (rc) return rc;
         pairs += c->m.pairs;
         bytes += c->m.intersect_bytes;
@@ -1055,15 +1452,31 @@ int gkd_query_vs_ref(gkd_ctx *c, const uint32_t *q, uint32_t nq, const uint32_t 
     c->m.intersect_ms = ims;
     c->m.epilogue_ms = ems;
     return GKD_OK;
+    ABI_GUARD_END(c)
 }
 
-int gkd_pairs(gkd_ctx *c, const uint32_t *a, const uint32_t *b, uint64_t n_pairs, uint64_t *inter, double *dist) {
+int gkd_query_vs_ref(gkd_ctx *c, const uint32_t *q, uint32_t nq, const uint32_t *r, uint32_t nr, uint64_t *inter, double *dist) {
+    gkd_outputs o{inter, dist, nullptr, nullptr};
+    return gkd_query_vs_ref_ex(c, q, nq, r, nr, &o);
+}
+
+int gkd_pairs_ex(gkd_ctx *c, const uint32_t *a, const uint32_t *b, uint64_t n_pairs, const gkd_outputs *out) {
     CHECK_CTX(c);
+    if (!out) return fail(c, GKD_EINVAL, "null outputs");
     CK(cudaSetDevice(c->cfg.device));
     if (n_pairs && (!a || !b)) return fail(c, GKD_EINVAL, "gkd_pairs: null id array");
     if (n_pairs > 0xFFFFFFFFull) return fail(c, GKD_EINVAL, "gkd_pairs: more than 2^32 pairs in one call");
+    int rc = lit_outputs_ok(c, *out);
+    if (rc) return rc;
+    ABI_GUARD_BEGIN
     HostPairs hp{PAIRS_LIST, 0, 0, n_pairs, a, b, (uint32_t)n_pairs, (uint32_t)n_pairs};
-    return run_pairs(c, hp, inter, dist);
+    return run_pairs(c, hp, *out);
+    ABI_GUARD_END(c)
+}
+
+int gkd_pairs(gkd_ctx *c, const uint32_t *a, const uint32_t *b, uint64_t n_pairs, uint64_t *inter, double *dist) {
+    gkd_outputs o{inter, dist, nullptr, nullptr};
+    return gkd_pairs_ex(c, a, b, n_pairs, &o);
 }
 
 int gkd_pair(gkd_ctx *c, uint32_t a, uint32_t b, uint64_t *inter, uint64_t *uni, double *dist) {

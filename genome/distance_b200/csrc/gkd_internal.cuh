@@ -12,20 +12,110 @@ namespace gkd {
 // Layout contracts
 // ------------------------------------------------------------------------------------------------
 // Key that is never a valid k-mer: the canonical form of t..t is a..a = 0, and eight 0xFF bytes are
-// not text.  Used for invalid k-mer slots before the sort and for the tail padding of every set.
+// not text.  Used for invalid k-mer slots before the sort.  The key mix below maps it to itself.
 constexpr uint64_t KEY_SENTINEL = 0xFFFFFFFFFFFFFFFFull;
 
-// Intersect kernel geometry.  A set in HBM is `n` sorted keys followed by sentinel keys up to
-// set_padded(n): the kernel stages fixed ISECT_BLK-key blocks with TMA bulk copies and relies on the
-// sentinels instead of bounds checks.  ISECT_W_MAX bounds the per-round window of every kernel
-// configuration (threads x keys-per-thread), so one padding rule serves them all.
-constexpr int ISECT_BLK = 512;       // keys per TMA bulk copy (4 KiB)
-constexpr int ISECT_W_MAX = 4096;    // largest per-round merge window of any configuration
+// ---- hashed key order ----------------------------------------------------------------------------
+// Sets are kept sorted by h = mix(key), a BIJECTION on the key_bits-bit keys (2K bits for DNA/RNA, 8K
+// for protein), not by the key itself.  Intersection only needs the two sets in the same total order,
+// and the mixed order makes every set uniform over the key space whatever the composition of the
+// genome (canonical k-mers are skewed towards a.. / c..; real genomes have GC bias and repeats), so
+// equal-width key ranges ("buckets") hold equal shares of every set: the merge partition of kernel 4
+// becomes a table lookup instead of a search, and kernel 3 can bucket by the top bits.
+// xorshift / odd-multiply rounds are each invertible modulo 2^bits; unmix() undoes them for export.
+struct MixParams {
+    uint64_t mask;  // 2^bits - 1
+    uint64_t fix;   // XOR constant that makes mix(all-ones key) == all-ones: that key is never valid (t..t is
+                    // canonically a..a; 0xFF bytes are not text), so no valid h shares the low bits of the sentinel
+    int bits;
+    int shift;      // ceil(bits / 2): x ^= x >> shift is then its own inverse
+};
 
-__host__ __device__ inline uint64_t set_padded(uint64_t n) {
-    // room for the window [i, i+W+1] at i == n, rounded to whole blocks
-    return ((n + ISECT_W_MAX + 2 + ISECT_BLK - 1) / ISECT_BLK) * (uint64_t)ISECT_BLK;
+constexpr uint64_t MIX_C1 = 0xff51afd7ed558ccdull, MIX_C2 = 0xc4ceb9fe1a85ec53ull;
+constexpr uint64_t MIX_I1 = 0x4f74430c22a54005ull, MIX_I2 = 0x9cb4b2f8129337dbull;  // inverses modulo 2^64
+
+__host__ __device__ inline uint64_t mix_rounds(uint64_t x, uint64_t mask, int s) {
+    x ^= x >> s;
+    x = (x * MIX_C1) & mask;
+    x ^= x >> s;
+    x = (x * MIX_C2) & mask;
+    x ^= x >> s;
+    return x;
 }
+__host__ __device__ inline uint64_t mix_key(uint64_t key, const MixParams &p) {
+    return mix_rounds(key, p.mask, p.shift) ^ p.fix;
+}
+__host__ __device__ inline uint64_t unmix_key(uint64_t h, const MixParams &p) {
+    uint64_t x = h ^ p.fix;
+    x ^= x >> p.shift;
+    x = (x * MIX_I2) & p.mask;
+    x ^= x >> p.shift;
+    x = (x * MIX_I1) & p.mask;
+    x ^= x >> p.shift;
+    return x;
+}
+inline MixParams make_mix(int bits) {
+    MixParams p;
+    p.bits = bits;
+    p.mask = bits >= 64 ? ~0ull : ((1ull << bits) - 1ull);
+    p.shift = (bits + 1) / 2;
+    if (p.shift < 1) p.shift = 1;
+    if (p.shift > 63) p.shift = 63;
+    p.fix = mix_rounds(p.mask, p.mask, p.shift) ^ p.mask;
+    return p;
+}
+
+// ---- bucketed set -----------------------------------------------------------------------------------
+// A finished set in HBM is
+//     offs[0 .. 2^level]  uint32   offs[b] = number of keys whose bucket (top `level` bits of h) is < b
+//     lows[0 .. n)        LowT     the keys in ascending h order, each stored as its low 32 bits
+//                                  (key_bits <= 42: a bucket at level >= key_bits-32 pins the rest) or
+//                                  as the full 64-bit h (wider keys)
+// `level` grows with the set so that a bucket holds at most `table_tmax` keys on average; levels are
+// nested powers of two, so any two sets can be walked bucket by bucket at the coarser of their levels
+// or any level below.  No sentinel tails: every run is bounded by its offsets.  Arrays start on 16-byte
+// boundaries and are followed by 16 readable bytes (TMA bulk copies move whole 16-byte units).
+struct SubSet {
+    const void *lows;
+    const uint32_t *offs;
+    uint32_t n;
+    uint32_t level;
+};
+// main = the canonical keys; pal = its reverse-palindromic members (even K, both-strand mode only)
+struct SetDesc {
+    SubSet main, pal;
+};
+
+constexpr uint32_t SET_LEVEL_MAX = 26;
+
+__host__ __device__ inline uint32_t ceil_log2_u32(uint32_t q) {  // smallest L with 2^L >= q
+    if (q <= 1) return 0;
+#ifdef __CUDA_ARCH__
+    return 32u - (uint32_t)__clz((int)(q - 1));
+#else
+    return 32u - (uint32_t)__builtin_clz(q - 1);
+#endif
+}
+// smallest level at which buckets of a set of n keys average at most tmax keys
+__host__ __device__ inline uint32_t level_for(uint32_t n, uint32_t tmax) { return ceil_log2_u32((n + tmax - 1) / tmax); }
+// lowest usable level of a context: the low word must pin every bit below the bucket bits
+__host__ __device__ inline uint32_t level_min(int key_bits, int low_bits) {
+    return key_bits > low_bits ? (uint32_t)(key_bits - low_bits) : 0u;
+}
+__host__ __device__ inline uint32_t level_cap(int key_bits) {
+    return (uint32_t)key_bits < SET_LEVEL_MAX ? (uint32_t)key_bits : SET_LEVEL_MAX;
+}
+__host__ __device__ inline uint32_t set_level(uint32_t n, uint32_t tmax, int key_bits, int low_bits) {
+    uint32_t l = level_for(n, tmax), lo = level_min(key_bits, low_bits), hi = level_cap(key_bits);
+    if (l < lo) l = lo;
+    if (l > hi) l = hi;
+    return l;
+}
+// 32-bit lows serve keys up to 42 bits (DNA/RNA K <= 21, protein K <= 5): the smallest table then has
+// 2^10 entries; wider keys keep the whole 64-bit h per key.
+inline int low_bits_for(int key_bits) { return key_bits <= 42 ? 32 : 64; }
+
+__host__ __device__ inline uint64_t align16(uint64_t x) { return (x + 15ull) & ~15ull; }
 
 // Packed residue streams.  A genome is one stream: its contigs joined by one separator position.
 // DNA/RNA: 2-bit codes a=0 c=1 g=2 t=3, 32 per uint64, position p at bits [2(p%32), +2) of word p/32,
@@ -58,14 +148,6 @@ struct BatchGenome {
     uint32_t n_tiles;
 };
 
-// Device-visible descriptor of a finished set.
-struct SetDesc {
-    const uint64_t *keys;
-    uint32_t n;
-    uint32_t n_pal;
-    const uint64_t *pal_keys;  // sorted palindromic members (padded like a set), or nullptr
-};
-
 // Pair enumeration modes of the intersect kernel
 enum PairMode : int { PAIRS_LIST = 0, PAIRS_UPPER = 1, PAIRS_RECT = 2 };
 
@@ -85,10 +167,10 @@ struct PairSource {
 cudaError_t launch_pack_dna(const char *text, uint64_t n_pos, uint64_t *codes, uint32_t *mask, int rna,
                             cudaStream_t s);
 cudaError_t launch_pack_prot(const char *text, uint64_t n_pos, uint8_t *codes, uint32_t *mask, cudaStream_t s);
-// kernel 2
+// kernel 2: writes h = mix(canonical key) per k-mer slot (KEY_SENTINEL for invalid slots)
 cudaError_t launch_encode(const BatchGenome *genomes, uint32_t n_genomes, uint32_t n_tiles, int alphabet, int k,
-                          uint64_t *keys_out, cudaStream_t s);
-// kernel 3: segmented LSD radix sort of each genome's slots, then unique/compact
+                          MixParams mix, uint64_t *keys_out, cudaStream_t s);
+// kernel 3: segmented LSD radix sort of each genome's slots, then unique/compact into bucketed sets
 struct SortPlan {
     uint32_t n_genomes, n_tiles;
     int key_bits;
@@ -97,29 +179,48 @@ struct SortPlan {
     uint64_t *tile_uniq;            // [n_tiles] packed (pal << 32 | uniq) counts -> exclusive offsets
     uint64_t *genome_counts;        // [n_genomes] packed totals
 };
+cudaError_t sort_configure();  // per-device function attributes; call once per context after cudaSetDevice
 cudaError_t launch_sort(const BatchGenome *genomes, const SortPlan &plan, uint64_t **sorted_out, uint32_t *passes,
                         cudaStream_t s);
 cudaError_t launch_unique_count(const BatchGenome *genomes, const SortPlan &plan, const uint64_t *sorted, int alphabet,
-                                int k, cudaStream_t s);
-struct UniqueDst {
-    uint64_t *keys;      // destination of the unique keys (set arena)
-    uint64_t *pal_keys;  // destination of palindromic keys (may be nullptr when n_pal == 0)
+                                int k, MixParams mix, cudaStream_t s);
+// where the unique pass writes one set (device pointers into the set arena)
+struct SetBuild {
+    void *lows;          // LowT[n]
+    uint32_t *offs;      // uint32[2^level + 1]
+    uint64_t *pal_h;     // scratch: full h of the palindromic members (n_pal entries), or nullptr
+    void *pal_lows;      // LowT[n_pal]
+    uint32_t *pal_offs;  // uint32[2^pal_level + 1]
+    uint32_t n, level, n_pal, pal_level;
 };
 cudaError_t launch_unique_write(const BatchGenome *genomes, const SortPlan &plan, const uint64_t *sorted,
-                                const UniqueDst *dst, int alphabet, int k, cudaStream_t s);
+                                const SetBuild *dst, int alphabet, int k, MixParams mix, int low_bits, cudaStream_t s);
+// in-place key -> h for imported key arrays (keys outside the key space become KEY_SENTINEL)
+cudaError_t launch_mix_keys(uint64_t *keys, uint64_t n, MixParams mix, cudaStream_t s);
+// bucketed set -> original keys (unsorted: ascending h order), for export
+cudaError_t launch_unmix_set(SubSet set, MixParams mix, int low_bits, uint64_t *keys_out, cudaStream_t s);
 cudaError_t launch_fill_u64(uint64_t *dst, uint64_t n, uint64_t value, cudaStream_t s);
 // kernels 4 + 5
-cudaError_t intersect_configure();
-cudaError_t launch_intersect(const SetDesc *sets, PairSource src, int use_pal, uint32_t seg_keys, uint32_t max_segs,
-                             uint32_t *counts, unsigned long long *work_counter, int n_sms, int algo, cudaStream_t s);
-cudaError_t launch_intersect_small(const SetDesc *sets, PairSource src, int use_pal, uint32_t *counts, int n_sms,
-                                   cudaStream_t s);
-uint32_t intersect_small_max_keys();  // sets up to this size take the warp-per-pair kernel
-int intersect_select(uint64_t min_keys, uint64_t max_keys, int key_bits);  // streaming kernel for this workload: 0 = CTA merge path, 1 = warp-cooperative
-int intersect_min_segment(int algo);   // smallest useful merge-path segment of that kernel
-int intersect_items_per_sm(int algo);  // work items per SM that keep that kernel's workers busy
+struct IsectPlan {
+    int low_bits;             // 32 or 64: lows type of the context
+    uint32_t tmax;            // lane target: a pair is walked at the smallest level where the larger set averages <= tmax keys per bucket
+    uint32_t level_min;       // lowest usable level of the context
+    uint32_t groups_per_item; // 32-bucket groups per work item
+    uint32_t items_per_pair;  // work items reserved per pair (items past a pair's last group exit at once)
+};
+cudaError_t intersect_configure();  // per-device function attributes; call once per context after cudaSetDevice
+uint32_t intersect_default_tmax(int low_bits);  // lane target the kernel is tuned for (sets the table resolution)
+uint32_t intersect_warps_per_sm(int low_bits);  // resident warps per SM of the selected configuration
+cudaError_t launch_intersect(const SetDesc *sets, PairSource src, int use_pal, const IsectPlan &plan, uint32_t *counts,
+                             unsigned long long *work_counter, int n_sms, cudaStream_t s);
+struct EpilogueOut {
+    uint64_t *inter;     // similarity() of the reference: |A n B| (both strands under GKD_STRAND_BOTH)
+    double *dist;        // SequenceKmers.distance
+    double *contain_a;   // I / |A|  (0 when |A| == 0)
+    double *contain_b;   // I / |B|
+};
 cudaError_t launch_epilogue(const SetDesc *sets, PairSource src, const uint32_t *counts, const uint32_t *pal_counts,
-                            int both_strands, uint64_t *inter, double *dist, cudaStream_t s);
+                            int both_strands, EpilogueOut out, cudaStream_t s);
 // synthetic data
 cudaError_t launch_synth(char *dst, uint64_t len, uint64_t seed, uint32_t family, uint32_t member, double rate,
                          int protein, cudaStream_t s);

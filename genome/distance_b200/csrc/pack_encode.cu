@@ -7,7 +7,8 @@
 //   Here both strands are represented by ONE canonical key min(fwd, revcomp) per position; the
 //   both-strand set sizes are recovered exactly as 2|C| - P (palindromes P counted in kernel 3).
 //   ProteinKmers: every K-substring, single strand (ProteinKmerReader.java:100-101); key = the K raw
-//   bytes, first character most significant, so key order is String order.
+//   bytes, first character most significant.
+//   Kernel 2 emits h = mix(key), the bijectively mixed key the sets are ordered by (gkd_internal.cuh).
 // Bound: HBM.  Algorithmic bytes: kernel 1 = 1 B read + 0.375 B written per residue (2-bit code +
 // 1-bit mask); kernel 2 = 0.375 B read + 8 B written per k-mer position.
 #include "gkd_internal.cuh"
@@ -122,7 +123,8 @@ constexpr int ENC_STRIDE = ENC_PER_THREAD + 1;  // smem padding: conflict-free 6
 
 template <int ALPHA>
 __global__ void __launch_bounds__(ENC_THREADS)
-    k_encode(const BatchGenome *__restrict__ genomes, uint32_t n_genomes, int k, uint64_t *__restrict__ keys_out) {
+    k_encode(const BatchGenome *__restrict__ genomes, uint32_t n_genomes, int k, MixParams mix,
+             uint64_t *__restrict__ keys_out) {
     __shared__ uint64_t stage[ENC_THREADS * ENC_STRIDE];
     __shared__ uint32_t s_g;
     if (threadIdx.x == 0) s_g = find_genome(genomes, n_genomes, blockIdx.x);
@@ -154,7 +156,7 @@ __global__ void __launch_bounds__(ENC_THREADS)
                 int j = r - (k - 1);  // slot completed by this byte
                 if (j >= 0 && j < ENC_PER_THREAD) {
                     bool ok = ((inv >> j) & kbits) == 0 && (my0 + j) < G.n_slots;
-                    mine[j] = ok ? key : KEY_SENTINEL;
+                    mine[j] = ok ? mix_key(key, mix) : KEY_SENTINEL;
                 }
             }
         } else {
@@ -179,7 +181,7 @@ __global__ void __launch_bounds__(ENC_THREADS)
                 uint64_t rc = (~v) & kmask;
                 uint64_t key = fwd < rc ? fwd : rc;
                 bool ok = ((inv >> j) & kbits) == 0 && (my0 + j) < G.n_slots;
-                mine[j] = ok ? key : KEY_SENTINEL;
+                mine[j] = ok ? mix_key(key, mix) : KEY_SENTINEL;  // sets are kept in mixed-key order
                 // slide one base: the 128-bit window shifts right by one code
                 lo = (lo >> 2) | (hi << 62);
                 hi >>= 2;
@@ -199,10 +201,10 @@ __global__ void __launch_bounds__(ENC_THREADS)
 }
 
 cudaError_t launch_encode(const BatchGenome *genomes, uint32_t n_genomes, uint32_t n_tiles, int alphabet, int k,
-                          uint64_t *keys_out, cudaStream_t s) {
+                          MixParams mix, uint64_t *keys_out, cudaStream_t s) {
     if (n_tiles == 0) return cudaSuccess;
-    if (alphabet == GKD_PROT) k_encode<GKD_PROT><<<n_tiles, ENC_THREADS, 0, s>>>(genomes, n_genomes, k, keys_out);
-    else k_encode<GKD_DNA><<<n_tiles, ENC_THREADS, 0, s>>>(genomes, n_genomes, k, keys_out);
+    if (alphabet == GKD_PROT) k_encode<GKD_PROT><<<n_tiles, ENC_THREADS, 0, s>>>(genomes, n_genomes, k, mix, keys_out);
+    else k_encode<GKD_DNA><<<n_tiles, ENC_THREADS, 0, s>>>(genomes, n_genomes, k, mix, keys_out);
     return cudaGetLastError();
 }
 

@@ -183,20 +183,19 @@ __global__ void __launch_bounds__(SORT_THREADS, 4)
     }
 }
 
-static bool g_scatter_configured = false;
+cudaError_t sort_configure() {
+    // per-device attribute: every context sets it after cudaSetDevice (a process-wide flag would leave a
+    // second device unconfigured)
+    return cudaFuncSetAttribute(k_radix_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)(SORT_TILE * sizeof(uint64_t)));
+}
 
 cudaError_t launch_sort(const BatchGenome *genomes, const SortPlan &plan, uint64_t **sorted_out, uint32_t *passes,
                         cudaStream_t s) {
     uint64_t *src = plan.keys_a, *dst = plan.keys_b;
     uint32_t np = 0;
-    if (!g_scatter_configured) {
-        cudaError_t e = cudaFuncSetAttribute(k_radix_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)(SORT_TILE * sizeof(uint64_t)));
-        if (e != cudaSuccess) return e;
-        g_scatter_configured = true;
-    }
     if (plan.n_tiles > 0 && plan.key_bits > 0) {
-        // fewest passes of at most RADIX_BITS bits, widths as even as possible (42 bits -> 9,9,8,8,8)
+        // fewest passes of at most RADIX_BITS bits, widths as even as possible (42 bits -> six 7-bit passes)
         const int n_pass = (plan.key_bits + RADIX_BITS - 1) / RADIX_BITS;
         const int base = plan.key_bits / n_pass, extra = plan.key_bits % n_pass;
         int shift = 0;
@@ -219,23 +218,25 @@ cudaError_t launch_sort(const BatchGenome *genomes, const SortPlan &plan, uint64
     return cudaGetLastError();
 }
 
-// ---- unique / compaction ---------------------------------------------------------------------------
+// ---- unique / compaction into bucketed sets ----------------------------------------------------------
 // packed flags of one sorted position: low word = "first occurrence of a real key", high word = "and
-// it is its own reverse complement"
+// the k-mer is its own reverse complement".  The sorted values are h = mix(key); the palindrome test
+// needs the key itself, so it un-mixes (even K only).
 __device__ __forceinline__ uint64_t unique_flags(const uint64_t *__restrict__ sorted, uint32_t idx, uint32_t n,
-                                                 bool check_pal, int k, uint64_t &key_out) {
+                                                 bool check_pal, int k, const MixParams &mix, uint64_t &h_out) {
     if (idx >= n) {
-        key_out = KEY_SENTINEL;
+        h_out = KEY_SENTINEL;
         return 0;
     }
-    uint64_t kx = sorted[idx];
-    key_out = kx;
-    if (kx == KEY_SENTINEL) return 0;
-    if (idx > 0 && sorted[idx - 1] == kx) return 0;
+    uint64_t h = sorted[idx];
+    h_out = h;
+    if (h == KEY_SENTINEL) return 0;
+    if (idx > 0 && sorted[idx - 1] == h) return 0;
     uint64_t f = 1;
     if (check_pal) {
-        uint64_t kmask = (k >= 32) ? ~0ull : ((1ull << (2 * k)) - 1);
-        uint64_t rc = (~(reverse_pairs(kx) >> (64 - 2 * k))) & kmask;
+        const uint64_t kx = unmix_key(h, mix);
+        const uint64_t kmask = (k >= 32) ? ~0ull : ((1ull << (2 * k)) - 1);
+        const uint64_t rc = (~(reverse_pairs(kx) >> (64 - 2 * k))) & kmask;
         if (rc == kx) f |= 1ull << 32;
     }
     return f;
@@ -243,7 +244,7 @@ __device__ __forceinline__ uint64_t unique_flags(const uint64_t *__restrict__ so
 
 __global__ void __launch_bounds__(SORT_THREADS)
     k_unique_count(const BatchGenome *__restrict__ genomes, uint32_t n_genomes, const uint64_t *__restrict__ sorted,
-                   uint64_t *__restrict__ tile_uniq, int check_pal, int k) {
+                   uint64_t *__restrict__ tile_uniq, int check_pal, int k, MixParams mix) {
     __shared__ uint64_t s_warp[SORT_WARPS];
     __shared__ uint32_t s_g;
     if (threadIdx.x == 0) s_g = find_genome(genomes, n_genomes, blockIdx.x);
@@ -251,10 +252,10 @@ __global__ void __launch_bounds__(SORT_THREADS)
     const BatchGenome G = genomes[s_g];
     const uint32_t slot0 = (blockIdx.x - G.tile_first) * SORT_TILE;
     const uint64_t *src = sorted + G.raw_off;
-    uint64_t acc = 0, kx;
+    uint64_t acc = 0, h;
 #pragma unroll 4
     for (int i = 0; i < SORT_ITEMS; i++)
-        acc += unique_flags(src, slot0 + i * SORT_THREADS + threadIdx.x, G.n_slots, check_pal != 0, k, kx);
+        acc += unique_flags(src, slot0 + i * SORT_THREADS + threadIdx.x, G.n_slots, check_pal != 0, k, mix, h);
     uint64_t total;
     block_exclusive_scan<uint64_t>(acc, s_warp, total);
     if (threadIdx.x == 0) tile_uniq[blockIdx.x] = total;
@@ -279,65 +280,151 @@ __global__ void __launch_bounds__(SORT_THREADS)
     if (threadIdx.x == 0) genome_counts[blockIdx.x] = carry;
 }
 
+// bucket of h at a table level (level 0 = one bucket)
+__device__ __forceinline__ uint32_t bucket_of(uint64_t h, int key_bits, uint32_t level) {
+    return level == 0 ? 0u : (uint32_t)(h >> (key_bits - (int)level));
+}
+
+// Writes the low words of the distinct keys in order and, from the same pass, the bucket offset table:
+// the thread that holds the first occurrence of a key also knows the previous distinct key (its left
+// neighbour in the sorted slots), so it fills the table entries of every bucket boundary between the
+// two; the thread of the last distinct key fills the tail.  Palindromic members go to a scratch list of
+// full h values that k_set_finish turns into the set's palindrome sub-set.
+template <typename LowT>
 __global__ void __launch_bounds__(SORT_THREADS)
     k_unique_write(const BatchGenome *__restrict__ genomes, uint32_t n_genomes, const uint64_t *__restrict__ sorted,
-                   const uint64_t *__restrict__ tile_uniq, const UniqueDst *__restrict__ dst, int check_pal, int k) {
+                   const uint64_t *__restrict__ tile_uniq, const SetBuild *__restrict__ dst, int check_pal, int k,
+                   MixParams mix) {
     __shared__ uint64_t s_warp[SORT_WARPS];
     __shared__ uint32_t s_g;
     if (threadIdx.x == 0) s_g = find_genome(genomes, n_genomes, blockIdx.x);
     __syncthreads();
     const BatchGenome G = genomes[s_g];
-    const UniqueDst D = dst[s_g];
+    const SetBuild D = dst[s_g];
+    LowT *lows = (LowT *)D.lows;
     const uint32_t slot0 = (blockIdx.x - G.tile_first) * SORT_TILE;
     const uint64_t *src = sorted + G.raw_off;
     uint64_t base = tile_uniq[blockIdx.x];
+    const uint32_t n_buckets = 1u << D.level;
     // chunks of 256 consecutive positions keep the output order == sorted order
     for (int i = 0; i < SORT_ITEMS; i++) {
-        uint64_t kx;
-        uint64_t f = unique_flags(src, slot0 + i * SORT_THREADS + threadIdx.x, G.n_slots, check_pal != 0, k, kx);
+        uint64_t h;
+        const uint32_t idx = slot0 + i * SORT_THREADS + threadIdx.x;
+        uint64_t f = unique_flags(src, idx, G.n_slots, check_pal != 0, k, mix, h);
         uint64_t total;
         uint64_t ex = block_exclusive_scan<uint64_t>(f, s_warp, total);
         if (f & 1ull) {
-            uint64_t at = base + ex;
-            D.keys[(uint32_t)at] = kx;
-            if (f >> 32) D.pal_keys[(uint32_t)(at >> 32)] = kx;
+            const uint64_t at64 = base + ex;
+            const uint32_t at = (uint32_t)at64;
+            lows[at] = (LowT)h;
+            if (f >> 32) D.pal_h[(uint32_t)(at64 >> 32)] = h;
+            const uint32_t b = bucket_of(h, mix.bits, D.level);
+            // entries (bucket of the previous distinct key, b] all start at this key
+            uint32_t q = idx == 0 ? 0u : bucket_of(src[idx - 1], mix.bits, D.level) + 1u;
+            for (; q <= b; q++) D.offs[q] = at;
+            if (at == D.n - 1u)
+                for (q = b + 1u; q <= n_buckets; q++) D.offs[q] = D.n;
         }
         base += total;
     }
 }
 
-// sentinel tail of every set written by k_unique_write
-__global__ void __launch_bounds__(256)
-    k_unique_pad(const UniqueDst *__restrict__ dst, const uint64_t *__restrict__ genome_counts) {
-    const UniqueDst D = dst[blockIdx.x];
-    uint64_t c = genome_counts[blockIdx.x];
-    uint32_t n = (uint32_t)c, np = (uint32_t)(c >> 32);
-    uint32_t end = (uint32_t)set_padded(n);
-    for (uint32_t i = n + threadIdx.x; i < end; i += blockDim.x) D.keys[i] = KEY_SENTINEL;
-    if (D.pal_keys) {
-        uint32_t pend = (uint32_t)set_padded(np);
-        for (uint32_t i = np + threadIdx.x; i < pend; i += blockDim.x) D.pal_keys[i] = KEY_SENTINEL;
+// one CTA per genome: the table of an empty set, and the palindrome sub-set (tiny: a k-mer is its own
+// reverse complement with probability 4^-(K/2)) built from the scratch list of full h values
+template <typename LowT>
+__global__ void __launch_bounds__(256) k_set_finish(const SetBuild *__restrict__ dst, MixParams mix) {
+    const SetBuild D = dst[blockIdx.x];
+    if (D.n == 0)
+        for (uint32_t q = threadIdx.x; q <= (1u << D.level); q += blockDim.x) D.offs[q] = 0;
+    if (D.pal_offs == nullptr) return;
+    LowT *pl = (LowT *)D.pal_lows;
+    for (uint32_t i = threadIdx.x; i < D.n_pal; i += blockDim.x) pl[i] = (LowT)D.pal_h[i];
+    for (uint32_t q = threadIdx.x; q <= (1u << D.pal_level); q += blockDim.x) {
+        // number of palindromic members whose bucket is < q
+        uint32_t lo = 0, hi = D.n_pal;
+        while (lo < hi) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (bucket_of(D.pal_h[mid], mix.bits, D.pal_level) < q) lo = mid + 1;
+            else hi = mid;
+        }
+        D.pal_offs[q] = lo;
     }
 }
 
 cudaError_t launch_unique_count(const BatchGenome *genomes, const SortPlan &plan, const uint64_t *sorted, int alphabet,
-                                int k, cudaStream_t s) {
+                                int k, MixParams mix, cudaStream_t s) {
     if (plan.n_genomes == 0) return cudaSuccess;
     int check_pal = (alphabet != GKD_PROT) && (k % 2 == 0);
     if (plan.n_tiles)
-        k_unique_count<<<plan.n_tiles, SORT_THREADS, 0, s>>>(genomes, plan.n_genomes, sorted, plan.tile_uniq, check_pal, k);
+        k_unique_count<<<plan.n_tiles, SORT_THREADS, 0, s>>>(genomes, plan.n_genomes, sorted, plan.tile_uniq, check_pal, k,
+                                                             mix);
     k_unique_scan<<<plan.n_genomes, SORT_THREADS, 0, s>>>(genomes, plan.tile_uniq, plan.genome_counts);
     return cudaGetLastError();
 }
 
 cudaError_t launch_unique_write(const BatchGenome *genomes, const SortPlan &plan, const uint64_t *sorted,
-                                const UniqueDst *dst, int alphabet, int k, cudaStream_t s) {
+                                const SetBuild *dst, int alphabet, int k, MixParams mix, int low_bits, cudaStream_t s) {
     if (plan.n_genomes == 0) return cudaSuccess;
     int check_pal = (alphabet != GKD_PROT) && (k % 2 == 0);
-    if (plan.n_tiles)
-        k_unique_write<<<plan.n_tiles, SORT_THREADS, 0, s>>>(genomes, plan.n_genomes, sorted, plan.tile_uniq, dst,
-                                                             check_pal, k);
-    k_unique_pad<<<plan.n_genomes, 256, 0, s>>>(dst, plan.genome_counts);
+    if (low_bits == 32) {
+        if (plan.n_tiles)
+            k_unique_write<uint32_t><<<plan.n_tiles, SORT_THREADS, 0, s>>>(genomes, plan.n_genomes, sorted, plan.tile_uniq,
+                                                                           dst, check_pal, k, mix);
+        k_set_finish<uint32_t><<<plan.n_genomes, 256, 0, s>>>(dst, mix);
+    } else {
+        if (plan.n_tiles)
+            k_unique_write<uint64_t><<<plan.n_tiles, SORT_THREADS, 0, s>>>(genomes, plan.n_genomes, sorted, plan.tile_uniq,
+                                                                           dst, check_pal, k, mix);
+        k_set_finish<uint64_t><<<plan.n_genomes, 256, 0, s>>>(dst, mix);
+    }
+    return cudaGetLastError();
+}
+
+// ---- import / export helpers -----------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_mix_keys(uint64_t *__restrict__ keys, uint64_t n, MixParams mix) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t kx = keys[i];
+        // a value outside the key space, or the all-ones key (never a valid k-mer, see MixParams::fix), cannot
+        // be a member of a set of this context: drop it (the sentinel sorts last)
+        keys[i] = ((kx & ~mix.mask) || kx == mix.mask) ? KEY_SENTINEL : mix_key(kx, mix);
+    }
+}
+
+cudaError_t launch_mix_keys(uint64_t *keys, uint64_t n, MixParams mix, cudaStream_t s) {
+    if (n == 0) return cudaSuccess;
+    uint64_t blocks = (n + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    k_mix_keys<<<(unsigned)blocks, 256, 0, s>>>(keys, n, mix);
+    return cudaGetLastError();
+}
+
+// one thread per key: find its bucket by binary search in the offset table, rebuild h, un-mix
+template <typename LowT>
+__global__ void __launch_bounds__(256) k_unmix_set(SubSet S, MixParams mix, uint64_t *__restrict__ keys_out) {
+    const LowT *lows = (const LowT *)S.lows;
+    const int rest = mix.bits - (int)S.level;  // bits of h below the bucket bits
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < S.n; i += gridDim.x * blockDim.x) {
+        uint64_t h = (uint64_t)lows[i];
+        if (sizeof(LowT) == 4 && S.level > 0) {
+            // largest bucket b with offs[b] <= i
+            uint32_t lo = 0, hi = 1u << S.level;
+            while (hi - lo > 1) {
+                const uint32_t mid = (lo + hi) >> 1;
+                if (S.offs[mid] <= i) lo = mid;
+                else hi = mid;
+            }
+            h = ((uint64_t)lo << rest) | (h & ((1ull << rest) - 1ull));
+        }
+        keys_out[i] = unmix_key(h, mix);
+    }
+}
+
+cudaError_t launch_unmix_set(SubSet set, MixParams mix, int low_bits, uint64_t *keys_out, cudaStream_t s) {
+    if (set.n == 0) return cudaSuccess;
+    uint32_t blocks = (set.n + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    if (low_bits == 32) k_unmix_set<uint32_t><<<blocks, 256, 0, s>>>(set, mix, keys_out);
+    else k_unmix_set<uint64_t><<<blocks, 256, 0, s>>>(set, mix, keys_out);
     return cudaGetLastError();
 }
 

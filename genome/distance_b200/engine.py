@@ -8,7 +8,12 @@ from typing import List, Sequence, Tuple
 import numpy as np
 
 from . import _lib
-from ._lib import DNA, PROT, RNA, STRAND_BOTH, STRAND_CANONICAL, GkdConfig, GkdMetrics
+from ._lib import (AMBIG_LITERAL, AMBIG_SKIP, DNA, PROT, RNA, STRAND_BOTH, STRAND_CANONICAL, GkdConfig, GkdMetrics,
+                   GkdOutputs, GkdPackedSet)
+
+PACKED_DTYPE = np.dtype([("offs_off", "<u8"), ("lows_off", "<u8"), ("pal_offs_off", "<u8"), ("pal_lows_off", "<u8"),
+                         ("n", "<u4"), ("n_pal", "<u4"), ("level", "<u4"), ("pal_level", "<u4")])
+assert PACKED_DTYPE.itemsize == C.sizeof(GkdPackedSet)
 
 
 class GkdError(RuntimeError):
@@ -31,10 +36,10 @@ class Engine:
     """
 
     def __init__(self, k: int = 0, alphabet: int = DNA, strand_mode: int = STRAND_BOTH, device: int = 0,
-                 workspace_bytes: int = 0, segment_keys: int = 0):
+                 workspace_bytes: int = 0, segment_keys: int = 0, ambig_policy: int = AMBIG_SKIP):
         self._L = _lib.load()
         cfg = GkdConfig(device=device, k=k, alphabet=alphabet, strand_mode=strand_mode,
-                        workspace_bytes=workspace_bytes, segment_keys=segment_keys)
+                        workspace_bytes=workspace_bytes, segment_keys=segment_keys, ambig_policy=ambig_policy)
         h = C.c_void_p()
         rc = self._L.gkd_create(C.byref(h), C.byref(cfg))
         if rc:
@@ -43,6 +48,7 @@ class Engine:
         self.device = device
         self.alphabet = alphabet
         self._keep: List[object] = []
+        self._adopted: List[Tuple[int, object]] = []  # (first id, buffer) of adopted panels
 
     # -- plumbing ---------------------------------------------------------------------------------
     def _ck(self, rc: int):
@@ -97,6 +103,8 @@ class Engine:
 
             torch.cuda.synchronize(self.device)  # producers ran on torch's stream
         self._ck(self._L.gkd_add_sequences(self._h, ptrs, lens, n, C.byref(out)))
+        # pinned / device text is read asynchronously and must stay alive until build() (gkd.h)
+        self._keep.extend(t[2] for t in triples if _is_torch(t[2]))
         return out.value
 
     def add_fasta(self, path: str, per_record: bool = True) -> Tuple[int, int]:
@@ -116,6 +124,7 @@ class Engine:
     # -- sets --------------------------------------------------------------------------------------
     def build(self):
         self._ck(self._L.gkd_build_sets(self._h))
+        self._keep.clear()
 
     def set_size(self, i: int) -> Tuple[int, int, int]:
         """(reference HashSet size, canonical count, palindromes)"""
@@ -130,26 +139,53 @@ class Engine:
         self._ck(self._L.gkd_export_set(self._h, i, out.ctypes.data if n else None, n, C.byref(got)))
         return out
 
-    def set_device_ptr(self, i: int) -> Tuple[int, int]:
-        p, n = C.c_void_p(), C.c_uint64()
-        self._ck(self._L.gkd_set_device_ptr(self._h, i, C.byref(p), C.byref(n)))
-        return (p.value or 0), n.value
+    # -- set exchange (multi-GPU) --------------------------------------------------------------------
+    def arenas(self) -> List[Tuple[int, int, int, int]]:
+        """[(first_id, n_sets, device address, bytes)] of every live set arena, in id order"""
+        out = []
+        for a in range(self._L.gkd_arena_count(self._h)):
+            first, n, base, nbytes = C.c_uint32(), C.c_uint32(), C.c_void_p(), C.c_uint64()
+            self._ck(self._L.gkd_arena_info(self._h, a, C.byref(first), C.byref(n), C.byref(base), C.byref(nbytes)))
+            out.append((first.value, n.value, base.value or 0, nbytes.value))
+        return out
 
-    def set_tensor(self, i: int):
-        """zero-copy 1-D int64 torch view of the sorted keys of set i on this context's device"""
+    def describe_sets(self, first_id: int, n_sets: int) -> np.ndarray:
+        """packed layout (PACKED_DTYPE, offsets relative to the arena base) of consecutive sets of one arena"""
+        table = np.zeros(n_sets, dtype=PACKED_DTYPE)
+        self._ck(self._L.gkd_describe_sets(self._h, first_id, n_sets,
+                                           table.ctypes.data_as(C.POINTER(GkdPackedSet))))
+        return table
+
+    def arena_meta(self):
+        """[(first_id, n_sets, bytes, table)] of every live arena: what sharding.plan_panels consumes"""
+        return [(first, n, nbytes, self.describe_sets(first, n)) for first, n, _, nbytes in self.arenas()]
+
+    def arena_view(self, arena: int, begin: int, end: int):
+        """zero-copy uint8 torch view of bytes [begin, end) of a set arena on this context's device
+        (aliases engine memory: send it, do not write it)"""
         import torch
 
-        ptr, n = self.set_device_ptr(i)
-        if n == 0:
-            return torch.empty(0, dtype=torch.int64, device=f"cuda:{self.device}")
+        base = self.arenas()[arena][2]
+        size = max(end - begin, 1)
 
         class _Raw:
-            __cuda_array_interface__ = {"shape": (n,), "typestr": "<i8", "data": (ptr, False), "version": 3}
+            __cuda_array_interface__ = {"shape": (size,), "typestr": "|u1", "data": (base + begin, False), "version": 3}
 
         return torch.as_tensor(_Raw(), device=f"cuda:{self.device}")
 
+    def adopt_sets(self, buf, table: np.ndarray) -> int:
+        """Register the sets described by `table` whose bytes are in `buf` (uint8 torch tensor on this
+        device, e.g. a received panel) WITHOUT copying; `buf` is kept alive until truncate()/reset().
+        The bytes must already be there (synchronise with the producer first)."""
+        t = np.ascontiguousarray(table, dtype=PACKED_DTYPE)
+        out = C.c_uint32()  # the caller has synchronised with whatever filled `buf`
+        self._ck(self._L.gkd_adopt_sets(self._h, buf.data_ptr(), buf.numel(), t.ctypes.data_as(C.POINTER(GkdPackedSet)),
+                                        t.size, C.byref(out)))
+        self._adopted.append((out.value, buf))
+        return out.value
+
     def import_set(self, keys) -> int:
-        """Adopt a sorted key array (numpy uint64 on host or torch int64/uint64 on this device)."""
+        """Add a set from its key array (numpy uint64 on host or torch int64/uint64 on this device); copied."""
         if isinstance(keys, np.ndarray):
             a = np.ascontiguousarray(keys, dtype=np.uint64)
             ptr, n, keep = a.ctypes.data, a.size, a
@@ -166,7 +202,7 @@ class Engine:
         return out.value
 
     def import_sets(self, keys, offsets) -> int:
-        """Adopt many sorted key arrays stored back to back (`keys`: numpy uint64 or torch int64 tensor,
+        """Add many sets from key arrays stored back to back (`keys`: numpy uint64 or torch int64 tensor,
         host or this device; `offsets`: n+1 host integers).  Returns the id of the first new set."""
         offs = np.ascontiguousarray(offsets, dtype=np.uint64)
         if isinstance(keys, np.ndarray):
@@ -222,6 +258,16 @@ class Engine:
         self._ck(self._L.gkd_pairs(self._h, aa.ctypes.data, ba.ctypes.data, aa.size, pi, pd))
         return inter, dist
 
+    def pairs_ex(self, a: Sequence[int], b: Sequence[int]):
+        """(inter, dist, contain_a, contain_b) of an explicit pair list (gkd_pairs_ex)"""
+        aa, ba = np.ascontiguousarray(a, dtype=np.uint32), np.ascontiguousarray(b, dtype=np.uint32)
+        n = aa.size
+        inter, dist = np.empty(n, dtype=np.uint64), np.empty(n, dtype=np.float64)
+        ca, cb = np.empty(n, dtype=np.float64), np.empty(n, dtype=np.float64)
+        o = GkdOutputs(inter.ctypes.data, dist.ctypes.data, ca.ctypes.data, cb.ctypes.data)
+        self._ck(self._L.gkd_pairs_ex(self._h, aa.ctypes.data, ba.ctypes.data, n, C.byref(o)))
+        return inter, dist, ca, cb
+
     def pair(self, a: int, b: int) -> Tuple[int, int, float]:
         i, u, d = C.c_uint64(), C.c_uint64(), C.c_double()
         self._ck(self._L.gkd_pair(self._h, a, b, C.byref(i), C.byref(u), C.byref(d)))
@@ -230,6 +276,8 @@ class Engine:
     # -- misc --------------------------------------------------------------------------------------
     def reset(self):
         self._ck(self._L.gkd_reset(self._h))
+        self._keep.clear()
+        self._adopted.clear()
 
     @property
     def stream_ptr(self) -> int:
@@ -249,6 +297,7 @@ class Engine:
     def truncate(self, n_keep: int):
         """drop the sets with id >= n_keep (a streamed panel) and recycle their arena"""
         self._ck(self._L.gkd_truncate(self._h, n_keep))
+        self._adopted = [x for x in self._adopted if x[0] < n_keep]
 
     def metrics(self) -> dict:
         m = GkdMetrics()

@@ -1,10 +1,10 @@
 """Multi-GPU sharding of the all-vs-all pair matrix (one process per GPU, torch.distributed).
 
 The path shards naturally: set construction is per genome, and the pair matrix has no
-cross-pair dependence and no reduction.  Rank r builds the sets of a contiguous slice of the genomes;
-ONE exchange step makes every set available on every rank (one broadcast per set from its owner,
-NCCL over NVLink on GPUs, gloo in the CPU tests); then rank r intersects a contiguous slice of the
-row-major strict-upper-triangle pair enumeration.  Results return to the host per rank.
+cross-pair dependence and no reduction.  Rank r builds the sets of a contiguous slice of the genomes and
+owns a set of rank blocks of the pair matrix; the sets of the peers it needs arrive as panels over NCCL
+send/recv (NVLink on GPUs, gloo in the CPU tests) while earlier blocks are being intersected, and are
+adopted in place (ring_all_vs_all below).  Results return to the host per rank.
 
 Everything here is host logic; it is exercised on CPU with gloo (tests/test_sharding_cpu.py) through
 the same functions the GPU bench uses.
@@ -70,83 +70,18 @@ def pair_lists(n: int, first: int, count: int) -> Tuple[np.ndarray, np.ndarray]:
     return a, b
 
 
-def exchange_sets(eng, n_genomes: int, world: int, rank: int, device) -> Dict[int, int]:
-    """Make every genome's key set resident in `eng` on every rank.
-
-    `eng` holds this rank's sets as ids 0..len(slice)-1 (built, in slice order) and must provide
-    `set_tensor(id) -> 1-D int64 torch tensor on `device`` and `import_set(tensor) -> id`.
-    Returns the map global genome index -> engine set id.
-    """
-    import torch
-    import torch.distributed as dist
-
-    mine = genome_slice(n_genomes, world, rank)
-    id_map = {g: i for i, g in enumerate(mine)}
-    # set sizes of every genome (one all_gather of a padded vector)
-    per = (n_genomes + world - 1) // world
-    sizes = torch.zeros(per, dtype=torch.int64, device=device)
-    for i in range(len(mine)):
-        sizes[i] = eng.set_tensor(i).numel()
-    all_sizes = [torch.zeros(per, dtype=torch.int64, device=device) for _ in range(world)]
-    dist.all_gather(all_sizes, sizes)
-    all_sizes = [t.cpu().tolist() for t in all_sizes]
-    if hasattr(eng, "import_sets") and hasattr(dist, "all_gather_into_tensor"):
-        # ONE collective: every rank packs its sets back to back into a send buffer padded to the
-        # largest per-rank total, all_gather_into_tensor moves them at full NVLink bandwidth, and each
-        # peer's segment is adopted with one batched import.
-        totals = [sum(int(x) for x in all_sizes[o][: len(genome_slice(n_genomes, world, o))]) for o in range(world)]
-        cap = max(max(totals), 1)
-        send = torch.empty(cap, dtype=torch.int64, device=device)
-        off = 0
-        for i in range(len(mine)):
-            t = eng.set_tensor(i)
-            send[off:off + t.numel()].copy_(t)
-            off += t.numel()
-        gathered = torch.empty(world * cap, dtype=torch.int64, device=device)
-        dist.all_gather_into_tensor(gathered, send)
-        del send
-        for owner in range(world):
-            if owner == rank:
-                continue
-            theirs = genome_slice(n_genomes, world, owner)
-            offs = np.zeros(len(theirs) + 1, dtype=np.uint64)
-            offs[1:] = np.cumsum(np.asarray([int(all_sizes[owner][li]) for li in range(len(theirs))], dtype=np.uint64))
-            first = eng.import_sets(gathered[owner * cap: owner * cap + int(offs[-1])], offs)
-            for li, g in enumerate(theirs):
-                id_map[g] = first + li
-        del gathered
-        return id_map
-    # generic path (any engine with import_set; used by the CPU/gloo tests): one broadcast per set
-    for owner in range(world):
-        theirs = genome_slice(n_genomes, world, owner)
-        sizes_o = [int(all_sizes[owner][li]) for li in range(len(theirs))]
-        if owner == rank:
-            for li in range(len(theirs)):
-                if sizes_o[li]:
-                    dist.broadcast(eng.set_tensor(li), src=owner)
-            continue
-        recv = torch.empty(max(max(sizes_o) if sizes_o else 0, 1), dtype=torch.int64, device=device)
-        for li, g in enumerate(theirs):
-            buf = recv[: sizes_o[li]]
-            if sizes_o[li]:
-                dist.broadcast(buf, src=owner)
-            id_map[g] = eng.import_set(buf)
-        del recv
-    return id_map
-
-
-def local_pair_ids(id_map: Dict[int, int], n_genomes: int, first: int, count: int) -> Tuple[np.ndarray, np.ndarray]:
-    """engine set ids of this rank's pair slice"""
-    a, b = pair_lists(n_genomes, first, count)
-    lut = np.empty(n_genomes, dtype=np.uint32)
-    for g, i in id_map.items():
-        lut[g] = i
-    return lut[a], lut[b]
-
-
 # ------------------------------------------------------------------------------------------------
-# Streamed column panels: all-vs-all when the sets do not fit one GPU (BASELINE config 4, SURVEY H1)
+# Panel ring: all-vs-all across ranks with the set exchange hidden behind the intersect kernel
 # ------------------------------------------------------------------------------------------------
+# Every rank keeps only its genome slice resident.  The pair matrix is cut into rank blocks; rank x owns
+# its diagonal block and the blocks (x, (x+s) mod R) for s = 1..R/2 (the half-way block of an even ring is
+# split between its two ranks), so it needs the sets of at most R/2 peers, one peer at a time.  A peer's
+# slice arrives as PANELS: byte ranges of the owner's set arenas (bucket tables + key low words exactly as
+# kernel 4 reads them), moved with NCCL send/recv over NVLink and adopted in place by the receiver
+# (gkd_adopt_sets: no unpack, no second copy).  The transfer of panel k+1 is posted before the kernels of
+# panel k are launched, so the only exposed transfer is the first one -- and that one runs under the
+# rank's diagonal block, which needs no remote data.  Every unordered pair of genomes is computed exactly
+# once; there is no reduction.  The same code serves config 2 (sets fit one GPU) and config 4 (they do not).
 def ring_partners(world: int, rank: int):
     """Steps s = 1..world//2 of the block ring: rank x owns block (x, (x+s) % world) and therefore
     receives the panel of src = (x+s) % world and sends its own to dst = (x-s) % world.  For even
@@ -169,40 +104,104 @@ def half_step_ranges(m_mine: int, m_partner: int, i_am_lower: bool):
     return (0, m_mine), (h, m_partner), (0, m_mine)
 
 
-def streamed_all_vs_all(eng, n_genomes: int, world: int, rank: int, device, panel_genomes: int = 256):
-    """All-vs-all without ever holding more than (own slice + one sub-panel) of sets per rank.
+def plan_panels(meta, lo: int, hi: int, max_sets: int):
+    """Panels that carry the local sets lo..hi-1 of a rank whose arenas are described by `meta`
+    (Engine.arena_meta(): [(first_id, n_sets, bytes, table)], table offsets relative to the arena base).
+    A panel never spans two arenas and holds at most max_sets sets.  Pure function of its arguments, so
+    the sender and the receiver derive the same plan.  Returns dicts: arena (index), first (local id),
+    count, begin/end (byte range inside the arena) and table (offsets relative to `begin`)."""
+    out = []
+    for ai, (first, n, nbytes, table) in enumerate(meta):
+        a, b = max(lo, first), min(hi, first + n)
+        while a < b:
+            m = min(b - a, max(1, max_sets))
+            t = np.array(table[a - first:a - first + m], copy=True)
+            begin = int(t["offs_off"][0])
+            end = int(nbytes) if a + m == first + n else int(table["offs_off"][a - first + m])
+            for f in ("offs_off", "lows_off"):
+                t[f] -= np.uint64(begin)
+            for f in ("pal_offs_off", "pal_lows_off"):
+                nz = t[f] != 0
+                t[f][nz] -= np.uint64(begin)
+            out.append({"arena": ai, "first": a, "count": m, "begin": begin, "end": end, "table": t})
+            a += m
+    return out
 
-    Every rank keeps its genome slice resident (built, ids 0..m-1), computes its diagonal block,
-    then walks the ring: the owner of a column panel sends it in sub-panels of `panel_genomes` sets
-    (NCCL send/recv over NVLink), the receiver adopts a sub-panel (`import_sets`), intersects
-    its rows against it (`query_vs_ref`), and drops it (`truncate`).  Every unordered pair of
-    genomes is computed exactly once somewhere; there is no reduction.
 
-    Returns this rank's results as (gi, gj, inter, dist) arrays with global ids gi < gj.
-    """
+def ring_all_vs_all(eng, n_genomes: int, world: int, rank: int, device, panel_genomes: int = 128, sink=None,
+                    stats=None):
+    """All-vs-all across `world` ranks (see the section comment).  `eng` holds this rank's genome slice
+    as built sets 0..m-1 and provides arena_meta / arena_view / adopt_sets / all_vs_all_range /
+    query_vs_ref / truncate.  `sink(gi, gj, inter, dist)` receives every block (global ids, row-major);
+    by default the blocks are collected and returned as (gi, gj, inter, dist) with gi < gj."""
+    import time
+
     import torch
     import torch.distributed as dist
 
+    on_gpu = torch.device(device).type == "cuda"
     mine = genome_slice(n_genomes, world, rank)
     m = len(mine)
-    per = (n_genomes + world - 1) // world
-    sizes = torch.zeros(per, dtype=torch.int64, device=device)
-    for i in range(m):
-        sizes[i] = eng.set_tensor(i).numel()
-    all_sizes = [torch.zeros(per, dtype=torch.int64, device=device) for _ in range(world)]
-    dist.all_gather(all_sizes, sizes)
-    all_sizes = [t.cpu().numpy() for t in all_sizes]
-
     out_i, out_j, out_inter, out_dist = [], [], [], []
 
-    def emit(rows, cols, inter, d):
+    def collect(rows, cols, inter, d):
         rows, cols = np.asarray(rows, dtype=np.int64), np.asarray(cols, dtype=np.int64)
         out_i.append(np.minimum(rows, cols))
         out_j.append(np.maximum(rows, cols))
         out_inter.append(np.asarray(inter).reshape(-1))
         out_dist.append(np.asarray(d).reshape(-1))
 
-    # diagonal block: my genomes against each other
+    emit = sink or collect
+    t_wait = 0.0
+
+    # everybody learns everybody's arena layout (a few KB per rank), so panel plans need no handshake
+    metas = [None] * world
+    if world > 1:
+        dist.all_gather_object(metas, eng.arena_meta())
+    else:
+        metas[0] = eng.arena_meta()
+
+    # flat list of transfer slots: (send panel | None, dst, recv panel | None, src, my rows, their slice)
+    slots = []
+    for src, dst, half in ring_partners(world, rank):
+        theirs = genome_slice(n_genomes, world, src)
+        if half:  # src == dst: the block is split between the two ranks
+            rows, recv_rng, send_rng = half_step_ranges(m, len(theirs), rank < src)
+        else:
+            rows, recv_rng, send_rng = (0, m), (0, len(theirs)), (0, m)
+        recv_list = plan_panels(metas[src], recv_rng[0], recv_rng[1], panel_genomes)
+        send_list = plan_panels(metas[rank], send_rng[0], send_rng[1], panel_genomes)
+        for k in range(max(len(recv_list), len(send_list))):
+            slots.append((send_list[k] if k < len(send_list) else None, dst,
+                          recv_list[k] if k < len(recv_list) else None, src, rows, theirs))
+
+    def post(slot):
+        """start the transfer of one slot (asynchronous on GPUs); one group per slot, so every rank's send
+        and receive are posted together and the ring cannot deadlock on unmatched point-to-point calls"""
+        send_p, dst, recv_p, src, rows, theirs = slot
+        ops, keep, buf = [], [], None
+        if send_p is not None:
+            view = eng.arena_view(send_p["arena"], send_p["begin"], send_p["end"])
+            keep.append(view)
+            ops.append(dist.P2POp(dist.isend, view, dst))
+        if recv_p is not None:
+            buf = torch.empty(max(recv_p["end"] - recv_p["begin"], 16), dtype=torch.uint8, device=device)
+            ops.append(dist.P2POp(dist.irecv, buf, src))
+        reqs = dist.batch_isend_irecv(ops) if ops else []
+        return reqs, buf, keep
+
+    def finish(reqs):
+        nonlocal t_wait
+        t0 = time.perf_counter()
+        for r in reqs:
+            r.wait()
+        if on_gpu:
+            torch.cuda.current_stream().synchronize()  # only what this stream waits for: the slot's transfer
+        t_wait += time.perf_counter() - t0
+
+    cur = post(slots[0]) if slots else None
+
+    # diagonal block: my genomes against each other (runs while the first panel is in flight)
     if m >= 2:
         cnt = m * (m - 1) // 2
         inter, d = eng.all_vs_all_range(m, 0, cnt)
@@ -210,47 +209,28 @@ def streamed_all_vs_all(eng, n_genomes: int, world: int, rank: int, device, pane
         base = mine[0]
         emit(a.astype(np.int64) + base, b.astype(np.int64) + base, inter, d)
 
-    for src, dst, half in ring_partners(world, rank):
-        theirs = genome_slice(n_genomes, world, src)
-        if half:  # src == dst: the block is split between the two ranks
-            rows, recv_rng, send_rng = half_step_ranges(m, len(theirs), rank < src)
-        else:
-            rows, recv_rng, send_rng = (0, m), (0, len(theirs)), (0, m)
-        my_rows = np.arange(rows[0], rows[1], dtype=np.uint32)
-        n_recv = (recv_rng[1] - recv_rng[0] + panel_genomes - 1) // panel_genomes
-        n_send = (send_rng[1] - send_rng[0] + panel_genomes - 1) // panel_genomes
-        for k in range(max(n_recv, n_send)):
-            ops, send, recv, offs, chunk = [], None, None, None, None
-            if k < n_send:
-                lo = send_rng[0] + k * panel_genomes
-                hi = min(send_rng[1], lo + panel_genomes)
-                parts = [eng.set_tensor(i) for i in range(lo, hi)]
-                send = torch.cat(parts) if parts else torch.empty(0, dtype=torch.int64, device=device)
-                if send.numel() == 0:
-                    send = torch.zeros(1, dtype=torch.int64, device=device)
-                ops.append(dist.P2POp(dist.isend, send, dst))
-            if k < n_recv:
-                li0 = recv_rng[0] + k * panel_genomes
-                li1 = min(recv_rng[1], li0 + panel_genomes)
-                chunk = theirs[li0:li1]
-                sz = all_sizes[src][li0:li1].astype(np.uint64)
-                offs = np.zeros(len(chunk) + 1, dtype=np.uint64)
-                offs[1:] = np.cumsum(sz)
-                recv = torch.empty(max(int(offs[-1]), 1), dtype=torch.int64, device=device)
-                ops.append(dist.P2POp(dist.irecv, recv, src))
-            # one NCCL group per sub-panel: every rank's send and receive are posted together, so the
-            # ring cannot deadlock on unmatched point-to-point calls
-            for r in (dist.batch_isend_irecv(ops) if ops else []):
-                r.wait()
-            if recv is not None and len(my_rows) > 0:
-                first = eng.import_sets(recv[: int(offs[-1])], offs)
-                cols = np.arange(first, first + len(chunk), dtype=np.uint32)
-                inter, d = eng.query_vs_ref(my_rows, cols)
-                rows_g = np.repeat(np.asarray(mine[rows[0]:rows[1]], dtype=np.int64), len(chunk))
-                cols_g = np.tile(np.asarray(chunk, dtype=np.int64), len(my_rows))
-                emit(rows_g, cols_g, inter, d)
-                eng.truncate(m)
-            del send, recv
+    for k, slot in enumerate(slots):
+        nxt = post(slots[k + 1]) if k + 1 < len(slots) else None  # in flight while panel k is intersected
+        reqs, buf, keep = cur
+        finish(reqs)
+        send_p, dst, recv_p, src, rows, theirs = slot
+        if recv_p is not None and rows[1] > rows[0]:
+            first = eng.adopt_sets(buf, recv_p["table"])
+            cols = np.arange(first, first + recv_p["count"], dtype=np.uint32)
+            my_rows = np.arange(rows[0], rows[1], dtype=np.uint32)
+            inter, d = eng.query_vs_ref(my_rows, cols)
+            chunk = theirs[recv_p["first"]:recv_p["first"] + recv_p["count"]]
+            rows_g = np.repeat(np.asarray(mine[rows[0]:rows[1]], dtype=np.int64), len(chunk))
+            cols_g = np.tile(np.asarray(chunk, dtype=np.int64), len(my_rows))
+            emit(rows_g, cols_g, inter, d)
+            eng.truncate(m)
+        del buf, keep
+        cur = nxt
+    if stats is not None:
+        stats["exposed_wait_s"] = t_wait
+        stats["slots"] = len(slots)
+    if sink is not None:
+        return None
     if not out_i:
         z = np.zeros(0, dtype=np.int64)
         return z, z, np.zeros(0, dtype=np.uint64), np.zeros(0, dtype=np.float64)

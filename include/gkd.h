@@ -13,9 +13,10 @@
  * Conventions
  *   - plain C types only; no exceptions or exit() cross the ABI; every call returns a gkd_status
  *     (0 = OK, negative = error class) and leaves a message retrievable with gkd_last_error().
- *   - caller owns every buffer it passes; inputs are consumed (copied to the device) before the
- *     call returns; outputs are caller-allocated.  Input sequence pointers may be pageable host,
- *     pinned host, or device memory (detected with cudaPointerGetAttributes).
+ *   - caller owns every buffer it passes; pageable host inputs are consumed (copied) before the call
+ *     returns, pinned-host and device sequence text by the next gkd_build_sets (see gkd_add_sequences);
+ *     outputs are caller-allocated.  Input sequence pointers may be pageable host, pinned host, or
+ *     device memory (detected with cudaPointerGetAttributes).
  *   - genomes/sequences are referred to by dense uint32 ids in insertion order.
  *   - a context is single-caller (not thread-safe); different contexts are independent.
  *   - there is NO CPU fallback: every entry point that computes fails with GKD_ECUDA when no
@@ -31,7 +32,7 @@
 extern "C" {
 #endif
 
-#define GKD_ABI_VERSION 1
+#define GKD_ABI_VERSION 2
 
 typedef enum gkd_status {
     GKD_OK = 0,
@@ -53,6 +54,15 @@ typedef enum gkd_alphabet { GKD_DNA = 0, GKD_PROT = 1, GKD_RNA = 2 } gkd_alphabe
  *   GKD_STRAND_CANONICAL - plain Jaccard over canonical k-mers (identical doubles for odd K)        */
 typedef enum gkd_strand_mode { GKD_STRAND_BOTH = 0, GKD_STRAND_CANONICAL = 1 } gkd_strand_mode;
 
+/* What to do with a nucleotide k-mer that contains a character outside acgt (after lower-casing; u reads
+ * as t for RNA).  The reference does not pin this ("low / unpinned"), so it is a switch:
+ *   GKD_AMBIG_SKIP    - the k-mer and its reverse complement are not members of the set
+ *   GKD_AMBIG_LITERAL - kept as a literal string (recalled upstream behaviour): the lower-cased window is
+ *                       a member and so is its reverse complement, in which the complement of an unknown
+ *                       base is 'n'.  Such k-mers are rare, so they live in a per-set side list that is
+ *                       built and intersected on the host; requires host-readable or device input text. */
+typedef enum gkd_ambig_policy { GKD_AMBIG_SKIP = 0, GKD_AMBIG_LITERAL = 1 } gkd_ambig_policy;
+
 typedef struct gkd_config {
     int32_t device;            /* CUDA device ordinal */
     int32_t k;                 /* k-mer size; 0 = type default (21 DNA/RNA, 8 protein;
@@ -60,9 +70,10 @@ typedef struct gkd_config {
     int32_t alphabet;          /* gkd_alphabet */
     int32_t strand_mode;       /* gkd_strand_mode */
     uint64_t workspace_bytes;  /* device scratch for set construction (0 = default 8 GiB cap) */
-    uint32_t segment_keys;     /* merge-path segment length in keys for the intersect kernel
-                                  (0 = choose from the workload) */
-    uint32_t reserved[7];
+    uint32_t segment_keys;     /* approximate keys (of both sets together) per work item of the intersect
+                                  kernel (0 = choose from the workload) */
+    int32_t ambig_policy;      /* gkd_ambig_policy (nucleotide alphabets only) */
+    uint32_t reserved[6];
 } gkd_config;
 
 typedef struct gkd_ctx gkd_ctx;
@@ -76,14 +87,17 @@ typedef struct gkd_metrics {
     uint64_t kmer_positions;    /* k-mer positions encoded by kernel 2 */
     uint64_t keys_sorted;       /* keys through the radix sort (kernel 3 input) */
     uint32_t sort_passes;       /* LSD passes per key */
-    uint32_t intersect_kernel;  /* kernel 4 variant of the last distance call: 0 = CTA merge path, 1 = warp-cooperative, 2 = small-set */
+    uint32_t intersect_kernel;  /* kernel 4 variant of the last distance call: 3 = bucket merge on 32-bit low words, 4 = on 64-bit keys */
     uint64_t keys_unique;       /* sum of |C| over the sets built */
     uint64_t pairs;             /* pairs intersected by the last distance call */
     uint64_t intersect_bytes;   /* ALGORITHMIC bytes of the last distance call: 8*(|C_A|+|C_B|) per pair */
     uint64_t h2d_bytes, d2h_bytes;
     uint64_t launches;          /* kernels launched by this ctx since creation */
     uint64_t intersect_launches;
-    uint64_t reserved[6];
+    uint64_t total_pairs;            /* the three "last distance call" figures summed since gkd_create / gkd_reset */
+    uint64_t total_intersect_bytes;
+    double total_intersect_ms;
+    uint64_t reserved[3];
 } gkd_metrics;
 
 /* ---- lifecycle --------------------------------------------------------------------------- */
@@ -102,6 +116,8 @@ int gkd_abi_version(void);
 
 /* ---- ingest: kernel 1 --------------------------------------------------------------------- */
 /* One genome / sequence record from n_contigs pieces; k-mers never span pieces.
+ * Pageable host text is consumed before the call returns.  Pinned-host and device text is read by
+ * stream-ordered copies: it must stay valid and unchanged until the next gkd_build_sets returns.
  * Stands behind: new GenomeKmers(genome) (GenomeProcessor.java:109,139 - one piece per contig),
  * KmerType.createKmers(seq, K) (FastaDistanceProcessor.java:153,184 - one piece),
  * new ProteinKmers(str) (ProteinKmerReader.java:100-101 - one piece; or one piece per protein for a
@@ -121,17 +137,41 @@ uint32_t gkd_count(const gkd_ctx *ctx);
 int gkd_build_sets(gkd_ctx *ctx);
 /* n_both = the reference's HashSet size (2|C|-P for DNA), n_canonical = |C|, n_palindromic = P */
 int gkd_set_size(const gkd_ctx *ctx, uint32_t id, uint64_t *n_both, uint64_t *n_canonical, uint64_t *n_palindromic);
-/* copy the sorted keys of one set to host memory (cap in keys); *n receives |C| */
+/* copy the keys of one set, sorted ascending, to host memory (cap in keys); *n receives |C|.  (The set is
+ * stored in mixed-key order; export un-mixes and sorts, so this is a test / cache path, not a fast one.) */
 int gkd_export_set(gkd_ctx *ctx, uint32_t id, uint64_t *keys, uint64_t cap, uint64_t *n);
-/* device address of the sorted keys of one set (for NCCL exchange by the host layer) */
-int gkd_set_device_ptr(const gkd_ctx *ctx, uint32_t id, const uint64_t **keys, uint64_t *n);
-/* adopt a prebuilt sorted key array (host or device pointer; copied) as a new set, e.g. one received
- * from another rank.  The unique/compact pass is re-run on it, which re-derives the palindrome list. */
+/* adopt a key array (host or device pointer; copied; any order, duplicates allowed) as a new set.  The
+ * keys go through the same mix / sort / unique pass as freshly encoded ones; values outside the key
+ * space of the context are dropped. */
 int gkd_import_set(gkd_ctx *ctx, const uint64_t *keys, uint64_t n, uint32_t *out_id);
 /* same for n_sets arrays stored back to back: set i is keys[offsets[i] .. offsets[i+1]) (offsets is a
- * HOST array of n_sets+1 entries; keys may be host or device memory).  One batched pass, one
- * synchronisation; ids first_id .. first_id+n_sets-1 are assigned in order. */
+ * HOST array of n_sets+1 entries; keys may be host or device memory).  ids first_id ..
+ * first_id+n_sets-1 are assigned in order. */
 int gkd_import_sets(gkd_ctx *ctx, const uint64_t *keys, const uint64_t *offsets, uint32_t n_sets, uint32_t *first_id);
+
+/* ---- set exchange between contexts / ranks (multi-GPU) ----------------------------
+ * Finished sets live in "arenas": one contiguous device allocation per build batch, sets back to back in
+ * id order, each set a position-independent block (bucket offset table + key low words, see DESIGN.md
+ * section 3).  A host layer moves whole arenas (or the byte range of consecutive sets) between GPUs with
+ * NCCL or peer copies and the receiver ADOPTS the bytes in place: no unpack, no second copy. */
+typedef struct gkd_packed_set {
+    uint64_t offs_off, lows_off;          /* byte offsets from the arena base: bucket table, key low words */
+    uint64_t pal_offs_off, pal_lows_off;  /* same for the palindrome sub-set (even K, both strands); 0 if none */
+    uint32_t n, n_pal;                    /* |C| and number of reverse-palindromic members */
+    uint32_t level, pal_level;            /* table levels: the tables have 2^level + 1 entries */
+} gkd_packed_set;
+uint32_t gkd_arena_count(const gkd_ctx *ctx);
+/* arena `arena` holds the sets first_id .. first_id+n_sets-1 in [base, base+bytes) on the context's device */
+int gkd_arena_info(const gkd_ctx *ctx, uint32_t arena, uint32_t *first_id, uint32_t *n_sets, const void **base,
+                   uint64_t *bytes);
+/* layout of n_sets consecutive sets of ONE arena, offsets relative to that arena's base */
+int gkd_describe_sets(const gkd_ctx *ctx, uint32_t first_id, uint32_t n_sets, gkd_packed_set *table);
+/* register n_sets sets whose bytes the caller placed at device address `base` (e.g. a received arena);
+ * `table` offsets are relative to `base`.  Nothing is copied: the caller keeps [base, base+bytes) alive and
+ * unchanged until the sets are dropped with gkd_truncate / gkd_reset / gkd_destroy.  The sets must come
+ * from a context with the same k, alphabet and strand mode. */
+int gkd_adopt_sets(gkd_ctx *ctx, const void *base, uint64_t bytes, const gkd_packed_set *table, uint32_t n_sets,
+                   uint32_t *first_id);
 
 /* persisted sorted-set cache (".kset"): every set of the context with its label and comment, so a
  * reference panel is built once.  Loading appends the sets as new ids and
@@ -152,6 +192,19 @@ int gkd_pairs(gkd_ctx *ctx, const uint32_t *a, const uint32_t *b, uint64_t n_pai
 /* Sub-range [first, first+count) of the row-major strict-upper-triangle pair enumeration of the
  * first n sets: the per-rank slice of the all-vs-all matrix. */
 int gkd_all_vs_all_range(gkd_ctx *ctx, uint32_t n, uint64_t first, uint64_t count, uint64_t *inter, double *dist);
+/* The same three calls with every output the epilogue can produce.  Any member may be NULL.
+ * contain_a = I / |A| and contain_b = I / |B| are the containment indices of the pair (0 for an empty set);
+ * they have no counterpart in the reference (north star: "Jaccard/containment"). */
+typedef struct gkd_outputs {
+    uint64_t *inter;
+    double *dist;
+    double *contain_a;
+    double *contain_b;
+} gkd_outputs;
+int gkd_all_vs_all_range_ex(gkd_ctx *ctx, uint32_t n, uint64_t first, uint64_t count, const gkd_outputs *out);
+int gkd_query_vs_ref_ex(gkd_ctx *ctx, const uint32_t *q, uint32_t nq, const uint32_t *r, uint32_t nr,
+                        const gkd_outputs *out);
+int gkd_pairs_ex(gkd_ctx *ctx, const uint32_t *a, const uint32_t *b, uint64_t n_pairs, const gkd_outputs *out);
 /* SequenceKmers.distance(other) for one pair (DistanceRepsProcessor.java:101,190;
  * FastaDistanceRepsProcessor.java:128); uni = |A|+|B|-I */
 int gkd_pair(gkd_ctx *ctx, uint32_t a, uint32_t b, uint64_t *inter, uint64_t *uni, double *dist);

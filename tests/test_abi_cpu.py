@@ -34,7 +34,7 @@ def test_library_exports_every_declared_symbol():
     lib = gkd.load()
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.gkd_abi_version() == 1
+    assert lib.gkd_abi_version() == _lib.ABI_VERSION == 2
 
 
 def test_structs_match_header_layout(tmp_path):
@@ -44,15 +44,17 @@ def test_structs_match_header_layout(tmp_path):
     src = tmp_path / "layout.c"
     src.write_text(
         '#include <stdio.h>\n#include <stddef.h>\n#include "gkd.h"\n'
-        'int main(void){printf("%zu %zu %zu %zu %zu %zu\\n", sizeof(gkd_config), offsetof(gkd_config, workspace_bytes),'
+        'int main(void){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(gkd_config), offsetof(gkd_config, workspace_bytes),'
         ' offsetof(gkd_config, segment_keys), sizeof(gkd_metrics), offsetof(gkd_metrics, keys_unique),'
-        ' offsetof(gkd_metrics, intersect_launches));return 0;}\n')
+        ' offsetof(gkd_metrics, intersect_launches), offsetof(gkd_config, ambig_policy), sizeof(gkd_packed_set),'
+        ' offsetof(gkd_packed_set, n), offsetof(gkd_packed_set, pal_level), sizeof(gkd_outputs));return 0;}\n')
     exe = tmp_path / "layout"
     subprocess.check_call(["gcc", "-std=c11", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
     got = [int(x) for x in subprocess.check_output([str(exe)]).split()]
-    cfg, met = _lib.GkdConfig, _lib.GkdMetrics
+    cfg, met, ps = _lib.GkdConfig, _lib.GkdMetrics, _lib.GkdPackedSet
     assert got == [C.sizeof(cfg), cfg.workspace_bytes.offset, cfg.segment_keys.offset, C.sizeof(met),
-                   met.keys_unique.offset, met.intersect_launches.offset]
+                   met.keys_unique.offset, met.intersect_launches.offset, cfg.ambig_policy.offset, C.sizeof(ps),
+                   ps.n.offset, ps.pal_level.offset, C.sizeof(_lib.GkdOutputs)]
 
 
 def test_format_double_matches_java_layout(orc):
@@ -98,7 +100,8 @@ def test_no_cpu_fallback_without_gpu():
 
 def test_bad_config_is_einval_or_ecuda():
     # argument validation happens before the device probe
-    for kw in (dict(k=33), dict(k=9, alphabet=gkd.PROT), dict(k=-1), dict(alphabet=7), dict(strand_mode=5)):
+    for kw in (dict(k=33), dict(k=9, alphabet=gkd.PROT), dict(k=-1), dict(alphabet=7), dict(strand_mode=5),
+               dict(ambig_policy=3)):
         with pytest.raises(gkd.GkdError) as e:
             gkd.Engine(**kw)
         assert e.value.code == _lib.GKD_EINVAL

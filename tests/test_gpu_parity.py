@@ -149,8 +149,8 @@ def test_all_vs_all_matches_command_oracle(orc):
 
 @pytest.mark.parametrize("k", [20, 21])
 def test_segmented_merge_path_is_exact(orc, k):
-    """Small merge-path segments (many (pair, segment) work items, global diagonal searches) must give
-    the same counts as whole-pair streaming and as the oracle -- including skewed sizes."""
+    """Small work items (many (pair, group-run) items per pair) must give the same counts as whole-pair
+    items and as the oracle -- including skewed sizes, where the sets meet at the larger one's level."""
     lens = [1200000, 1200000, 90000, 2500000, 40]
     seqs = []
     for g, n in enumerate(lens):
@@ -236,9 +236,11 @@ def test_import_export_and_ranges(orc):
             e.add(s)
         e.build()
         gi, gd = e.all_vs_all()
-        # ship the sets to a second context (the multi-GPU exchange path) and compare
+        # ship the keys to a second context and compare (shuffled and with duplicates: import sorts)
         for i in range(len(seqs)):
-            f.import_set(e.export_set(i))
+            keys = e.export_set(i)
+            assert (np.diff(keys.astype(np.int64)) > 0).all()
+            f.import_set(np.concatenate([keys[::-1], keys[:7]]))
         fi, fd = f.all_vs_all()
         assert np.array_equal(fi, gi) and np.array_equal(fd, gd)
         # any contiguous slice of the pair enumeration reproduces the same numbers
@@ -340,7 +342,8 @@ def test_config5_shape_skewed_sizes(orc):
 
 @pytest.mark.parametrize("k,alpha", [(21, "DNA"), (12, "DNA"), (8, "PROT")])
 def test_many_small_sequences_all_vs_all(orc, k, alpha):
-    """fastaDist's own use case: hundreds of gene/protein-sized records (warp-per-pair kernel)."""
+    """fastaDist's own use case: hundreds of gene/protein-sized records (tiny sets: every pair is one or a
+    few 32-bucket groups at the lowest table level)."""
     rng = random.Random(900 + k)
     letters = "ACDEFGHIKLMNPQRSTVWY" if alpha == "PROT" else "acgt"
     al = gkd.PROT if alpha == "PROT" else gkd.DNA
@@ -425,19 +428,26 @@ def test_fuzz_against_oracle(orc):
                 t += 1
 
 
-@pytest.mark.parametrize("algo", ["cta", "warp"])
-def test_both_streaming_kernels_are_exact(orc, algo, monkeypatch):
-    """GKD_ISECT_ALGO pins the streaming kernel (auto picks by size balance): the CTA merge-path kernel
-    and the warp-cooperative ballot kernel must both be exact on balanced AND skewed pairs, whole and
-    segmented (the env var is read when a context is created)."""
-    monkeypatch.setenv("GKD_ISECT_ALGO", algo)
+@pytest.mark.parametrize("cfg,tmax,table_tmax", [("0", None, None), ("1", None, None), ("2", None, None),
+                                                 ("3", None, None), ("4", None, None), ("5", None, None),
+                                                 ("0", "64", "16"), ("0", "3", "2"), ("2", "16", "4")])
+def test_every_kernel4_configuration_is_exact(orc, cfg, tmax, table_tmax, monkeypatch):
+    """GKD_ISECT_CFG pins the stage geometry of kernel 4, GKD_ISECT_TMAX / GKD_TABLE_TMAX the lane target and
+    the table resolution (read when a context is created).  Every configuration must be exact on balanced
+    AND skewed pairs, whole and split into small work items -- including lane targets that overflow the
+    shared-memory stage (tmax 64: the groups are merged straight from global memory), tables finer than
+    the walk level, and walk levels capped by a coarse table."""
+    monkeypatch.setenv("GKD_ISECT_CFG", cfg)
+    if tmax:
+        monkeypatch.setenv("GKD_ISECT_TMAX", tmax)
+        monkeypatch.setenv("GKD_TABLE_TMAX", table_tmax)
     lens = [600_000, 610_000, 590_000, 30_000, 1_400_000, 25]
     seqs = []
     for g, n in enumerate(lens):
         a = np.empty(n, dtype=np.uint8)
         gkd.synth(a, 123, g % 2, g // 2, 0.03 if g // 2 else 0.0)
         seqs.append(a.tobytes())
-    for k in (21, 16):
+    for k in (21, 16, 25):
         osets = [orc.IntSet(s, k) for s in seqs]
         want_i = [osets[i].similarity(osets[j]) for i in range(len(seqs)) for j in range(i + 1, len(seqs))]
         want_d = [osets[i].distance(osets[j]) for i in range(len(seqs)) for j in range(i + 1, len(seqs))]
@@ -447,4 +457,59 @@ def test_both_streaming_kernels_are_exact(orc, algo, monkeypatch):
                     e.add(s)
                 e.build()
                 gi, gd = e.all_vs_all()
-            assert gi.tolist() == want_i and gd.tolist() == want_d, (algo, k, seg)
+            assert gi.tolist() == want_i and gd.tolist() == want_d, (cfg, tmax, k, seg)
+
+
+def test_containment_outputs(orc):
+    seqs = _np_family(77, 6, 50000, [0.01, 0.1])
+    for k in (21, 12):
+        with gkd.Engine(k=k) as e:
+            for s in seqs:
+                e.add(s)
+            e.build()
+            a = [i for i in range(len(seqs)) for j in range(len(seqs))]
+            b = [j for i in range(len(seqs)) for j in range(len(seqs))]
+            inter, dist, ca, cb = e.pairs_ex(a, b)
+            sizes = [e.set_size(i)[0] for i in range(len(seqs))]
+        for t, (i, j) in enumerate(zip(a, b)):
+            assert ca[t] == int(inter[t]) / sizes[i] and cb[t] == int(inter[t]) / sizes[j]
+            if i == j:
+                assert ca[t] == 1.0 and dist[t] == 0.0
+
+
+def test_packed_sets_are_adopted_in_place(orc):
+    """the multi-GPU exchange path on one device: describe the arenas of one context, copy their bytes,
+    adopt them in a second context without unpacking, and get the same answers"""
+    import torch
+
+    from genome.distance_b200 import sharding
+
+    seqs = _np_family(5, 9, 60000, [0.01, 0.05])
+    for k in (21, 20):  # even K: the palindrome sub-sets travel too
+        with gkd.Engine(k=k, workspace_bytes=4 << 20) as e, gkd.Engine(k=k) as f:
+            for s in seqs:
+                e.add(s)
+            e.build()
+            assert len(e.arenas()) > 1  # the small workspace forces several build batches
+            gi, gd = e.all_vs_all()
+            meta = e.arena_meta()
+            bufs = []
+            for p in sharding.plan_panels(meta, 0, len(seqs), 2):
+                buf = e.arena_view(p["arena"], p["begin"], p["end"]).clone()
+                torch.cuda.synchronize()
+                first = f.adopt_sets(buf, p["table"])
+                assert first == p["first"]
+                bufs.append(buf)
+            assert [f.set_size(i) for i in range(len(seqs))] == [e.set_size(i) for i in range(len(seqs))]
+            fi, fd = f.all_vs_all()
+            assert np.array_equal(fi, gi) and np.array_equal(fd, gd)
+            assert np.array_equal(f.export_set(3), e.export_set(3))
+            f.truncate(4)
+            hi, hd = f.all_vs_all()
+            assert np.array_equal(hi, gi[[0, 1, 2, 8, 9, 15]]) and len(f) == 4
+            # a descriptor that does not fit the buffer is refused
+            bad = sharding.plan_panels(meta, 0, 1, 1)[0]["table"].copy()
+            bad["lows_off"] += np.uint64(1 << 40)
+            with pytest.raises(gkd.GkdError) as err:
+                f.adopt_sets(bufs[0], bad)
+            assert err.value.code == -1

@@ -1,5 +1,6 @@
-"""Host-side multi-GPU logic on CPU: partitions, pair enumeration, and the world_size-2 set exchange
-over gloo through the same functions the GPU bench uses (the compute stand-in is the oracle)."""
+"""Host-side multi-GPU logic on CPU: partitions, pair enumeration, panel plans, and the overlapped panel
+ring over gloo at world sizes 2-4 through the same functions the GPU bench uses (the compute stand-in is
+the oracle)."""
 import os
 import socket
 
@@ -45,21 +46,6 @@ def test_pair_lists_match_row_major_order():
             sharding.pair_lists(n, total, 1)
 
 
-class _CpuEngine:
-    """stand-in with the two methods exchange_sets needs; sets are the oracle's key arrays"""
-
-    def __init__(self, orc, seqs, k):
-        self.orc = orc
-        self.sets = [torch.from_numpy(orc.IntSet(s, k).keys().astype(np.int64)) for s in seqs]
-
-    def set_tensor(self, i):
-        return self.sets[i]
-
-    def import_set(self, t):
-        self.sets.append(t.clone())
-        return len(self.sets) - 1
-
-
 def _seqs(n, length):
     import genome.distance_b200 as gkd
 
@@ -69,52 +55,6 @@ def _seqs(n, length):
         gkd.synth(a, 99, g % 2, g // 2, 0.03 if g // 2 else 0.0)
         out.append(a.tobytes())
     return out
-
-
-def _worker(rank, world, port, n, length, k, ret):
-    os.environ["MASTER_ADDR"] = "127.0.0.1"
-    os.environ["MASTER_PORT"] = str(port)
-    dist.init_process_group("gloo", rank=rank, world_size=world)
-    from oracle import oracle as orc
-
-    seqs = _seqs(n, length)
-    mine = sharding.genome_slice(n, world, rank)
-    eng = _CpuEngine(orc, [seqs[g] for g in mine], k)
-    id_map = sharding.exchange_sets(eng, n, world, rank, torch.device("cpu"))
-    assert sorted(id_map) == list(range(n))
-    total = n * (n - 1) // 2
-    first, count = sharding.pair_slice(total, world, rank)
-    ia, ib = sharding.local_pair_ids(id_map, n, first, count)
-    out = torch.zeros(total, dtype=torch.int64)
-    for t in range(count):
-        x, y = eng.sets[ia[t]].numpy(), eng.sets[ib[t]].numpy()
-        out[first + t] = np.intersect1d(x, y, assume_unique=True).size
-    dist.all_reduce(out)  # disjoint slices: the sum is the concatenation (test-only gather)
-    if rank == 0:
-        ret.put(out.tolist())
-    dist.destroy_process_group()
-
-
-@pytest.mark.parametrize("world", [2, 3])
-def test_exchange_and_pair_slices_over_gloo(orc, world):
-    n, length, k = 7, 20000, 15
-    s = socket.socket()
-    s.bind(("127.0.0.1", 0))
-    port = s.getsockname()[1]
-    s.close()
-    ctx = mp.get_context("spawn")
-    ret = ctx.Queue()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, n, length, k, ret), daemon=True) for r in range(world)]
-    for p in procs:
-        p.start()
-    got = ret.get(timeout=120)
-    for p in procs:
-        p.join(timeout=60)
-        assert p.exitcode == 0
-    seqs = _seqs(n, length)
-    sets = [orc.IntSet(x, k) for x in seqs]
-    want = [sets[i].intersect(sets[j])[0] for i in range(n) for j in range(i + 1, n)]
-    assert got == want
 
 
 def test_ring_partners_cover_every_rank_pair_once():
@@ -138,19 +78,49 @@ def test_ring_partners_cover_every_rank_pair_once():
         assert (rows_l[1] - rows_l[0]) + (recv_h[1] - recv_h[0]) == m_lo and rows_h == (0, m_hi)
 
 
-class _CpuPanelEngine(_CpuEngine):
-    """adds the batched calls streamed_all_vs_all needs (numpy stand-ins for kernels 4-5)"""
+class _CpuPanelEngine:
+    """CPU stand-in for gkd.Engine with the calls ring_all_vs_all needs.  Sets are the oracle's key arrays;
+    an "arena" is a uint8 tensor that holds the keys of `per_arena` consecutive sets back to back, each
+    block padded to 16 bytes, described with the engine's packed-set table (numpy stand-ins for kernels 4-5)."""
+
+    def __init__(self, orc, seqs, k, per_arena=2):
+        from genome.distance_b200.engine import PACKED_DTYPE
+
+        self.orc = orc
+        self.sets = [orc.IntSet(s, k).keys().astype(np.int64) for s in seqs]
+        self.own = []  # (first, n, uint8 tensor, table)
+        for first in range(0, len(self.sets), per_arena):
+            chunk = self.sets[first:first + per_arena]
+            table = np.zeros(len(chunk), dtype=PACKED_DTYPE)
+            blobs, off = [], 0
+            for i, keys in enumerate(chunk):
+                raw = keys.tobytes() + b"\0" * ((-keys.nbytes) % 16 + 16)
+                table[i]["offs_off"] = table[i]["lows_off"] = off
+                table[i]["n"] = keys.size
+                blobs.append(raw)
+                off += len(raw)
+            self.own.append((first, len(chunk), torch.frombuffer(bytearray(b"".join(blobs)), dtype=torch.uint8), table))
+        self.adopted_buffers = 0
+
+    def arena_meta(self):
+        return [(first, n, t.numel(), table) for first, n, t, table in self.own]
+
+    def arena_view(self, arena, begin, end):
+        return self.own[arena][2][begin:max(end, begin + 1)]
+
+    def adopt_sets(self, buf, table):
+        first = len(self.sets)
+        raw = buf.numpy().tobytes()
+        for row in table:
+            lo = int(row["lows_off"])
+            self.sets.append(np.frombuffer(raw[lo:lo + 8 * int(row["n"])], dtype=np.int64))
+        self.adopted_buffers += 1
+        return first
 
     def _pair(self, i, j):
-        x, y = self.sets[i].numpy(), self.sets[j].numpy()
+        x, y = self.sets[i], self.sets[j]
         inter = 2 * np.intersect1d(x, y, assume_unique=True).size  # odd K: both-strand count
         return inter, self.orc.distance(inter, 2 * x.size, 2 * y.size)
-
-    def import_sets(self, t, offs):
-        first = len(self.sets)
-        for a, b in zip(offs[:-1], offs[1:]):
-            self.sets.append(t[int(a):int(b)].clone())
-        return first
 
     def truncate(self, n):
         del self.sets[n:]
@@ -166,7 +136,27 @@ class _CpuPanelEngine(_CpuEngine):
                 np.array([[x[1] for x in row] for row in res], dtype=np.float64).reshape(len(q), len(r)))
 
 
-def _stream_worker(rank, world, port, n, length, k, panel, ret):
+def test_plan_panels_is_a_partition():
+    from genome.distance_b200.engine import PACKED_DTYPE
+
+    meta = []
+    first = 0
+    for n in (3, 1, 4):
+        table = np.zeros(n, dtype=PACKED_DTYPE)
+        table["offs_off"] = np.arange(n) * 256
+        table["lows_off"] = table["offs_off"] + 32
+        meta.append((first, n, n * 256, table))
+        first += n
+    for lo, hi, mx in ((0, 8, 2), (1, 7, 3), (2, 3, 1), (5, 5, 4), (0, 8, 100)):
+        plan = sharding.plan_panels(meta, lo, hi, mx)
+        ids = [i for p in plan for i in range(p["first"], p["first"] + p["count"])]
+        assert ids == list(range(lo, hi))
+        for p in plan:
+            assert p["count"] <= mx and p["table"]["offs_off"][0] == 0 and p["end"] > p["begin"]
+            assert (p["table"]["lows_off"] - p["table"]["offs_off"] == 32).all()
+
+
+def _ring_worker(rank, world, port, n, length, k, panel, ret):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -175,15 +165,18 @@ def _stream_worker(rank, world, port, n, length, k, panel, ret):
     seqs = _seqs(n, length)
     mine = sharding.genome_slice(n, world, rank)
     eng = _CpuPanelEngine(orc, [seqs[g] for g in mine], k)
-    gi, gj, inter, d = sharding.streamed_all_vs_all(eng, n, world, rank, torch.device("cpu"), panel_genomes=panel)
-    assert len(eng.sets) == len(mine)  # every streamed panel was dropped again
+    stats = {}
+    gi, gj, inter, d = sharding.ring_all_vs_all(eng, n, world, rank, torch.device("cpu"), panel_genomes=panel, stats=stats)
+    assert len(eng.sets) == len(mine)  # every received panel was dropped again
     ret.put((rank, gi.tolist(), gj.tolist(), [int(x) for x in inter], d.tolist()))
     dist.barrier()
     dist.destroy_process_group()
 
 
 @pytest.mark.parametrize("world,panel", [(2, 2), (3, 1), (4, 3)])
-def test_streamed_panels_over_gloo(orc, world, panel):
+def test_ring_all_vs_all_over_gloo(orc, world, panel):
+    """world_size 2-4 on CPU: panels planned from the owners' arena layouts, moved with send/recv, adopted,
+    intersected and dropped; every pair computed exactly once and equal to the oracle"""
     n, length, k = 9, 12000, 15
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
@@ -191,7 +184,7 @@ def test_streamed_panels_over_gloo(orc, world, panel):
     s.close()
     ctx = mp.get_context("spawn")
     ret = ctx.Queue()
-    procs = [ctx.Process(target=_stream_worker, args=(r, world, port, n, length, k, panel, ret), daemon=True)
+    procs = [ctx.Process(target=_ring_worker, args=(r, world, port, n, length, k, panel, ret), daemon=True)
              for r in range(world)]
     for p in procs:
         p.start()

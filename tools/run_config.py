@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Run one BASELINE.json config at full size on one B200 and print a JSON line for BASELINE.md section 5.
 
-  c1  2 x 5 Mbp DNA K=21, one pair (merge-path segments fill the GPU)
+  c1  2 x 5 Mbp DNA K=21, one pair (its 32-bucket groups are spread over every warp of the GPU)
   c3  protein K=8: 10,000 query x 500 reference genomes, ~4,000 proteins each (per-genome union sets)
   c5  2,000 genomes with log-uniform lengths in [100 kbp, 12 Mbp], all-vs-all
 
@@ -22,7 +22,11 @@ import genome.distance_b200 as gkd
 from oracle import oracle as orc
 
 SEED = 0x5EED0000
-PEAK = 6547.5
+_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+try:
+    PEAK = float(json.load(open(os.path.join(_ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+except Exception:
+    PEAK = 6650.0  # fallback of B200_PROFILING.md
 
 
 def finish(name, eng, pairs, t_build, t_dist, extra):
@@ -33,7 +37,7 @@ def finish(name, eng, pairs, t_build, t_dist, extra):
            "intersect_ms": m["intersect_ms"], "intersect_algorithmic_GBps": gbs, "intersect_frac_of_hbm": gbs / PEAK,
            "sort_passes": m["sort_passes"], "keys_unique": m["keys_unique"]}
     out.update(extra)
-    print(json.dumps(out), flush=True)
+    return out
 
 
 def c1():
@@ -52,7 +56,7 @@ def c1():
         h = dev.cpu().numpy()
         oa, ob = orc.IntSet(h[0].tobytes(), 21), orc.IntSet(h[1].tobytes(), 21)
         ok = int(inter[0]) == oa.similarity(ob) and dist[0] == oa.distance(ob)
-        finish("c1: 2 x 5 Mbp DNA K=21", e, 1, t1 - t0, t2 - t1, {"distance": gkd.format_double(float(dist[0])), "oracle_match": bool(ok)})
+        return finish("c1: 2 x 5 Mbp DNA K=21", e, 1, t1 - t0, t2 - t1, {"distance": gkd.format_double(float(dist[0])), "oracle_match": bool(ok)})
 
 
 def c3(nq, nr, n_prot):
@@ -85,7 +89,7 @@ def c3(nq, nr, n_prot):
         for (a, b) in ((0, 0), (1, 0)):
             qa, rb = e.export_set(qid[a]), e.export_set(rid[b])
             ok &= int(inter[a, b]) == int(np.intersect1d(qa, rb, assume_unique=True).size)
-        finish(f"c3: protein K=8, {nq} queries x {nr} refs, {n_prot} proteins/genome", e, nq * nr, t1 - t0, t2 - t1,
+        return finish(f"c3: protein K=8, {nq} queries x {nr} refs, {n_prot} proteins/genome", e, nq * nr, t1 - t0, t2 - t1,
                {"residues_per_genome": total, "frac_pairs_related": float((dist < 1.0).mean()), "oracle_match": bool(ok)})
 
 
@@ -110,7 +114,7 @@ def c5(n):
         a, b = e.export_set(0), e.export_set(20)  # same family, different lengths
         t = 19  # pair (0, 20) in row-major order
         ok = int(inter[t]) == 2 * int(np.intersect1d(a, b, assume_unique=True).size)
-        finish(f"c5: {n} genomes log-uniform 100 kbp..12 Mbp all-vs-all", e, n * (n - 1) // 2, t1 - t0, t2 - t1,
+        return finish(f"c5: {n} genomes log-uniform 100 kbp..12 Mbp all-vs-all", e, n * (n - 1) // 2, t1 - t0, t2 - t1,
                {"total_bp": int(lens.sum()), "oracle_match": bool(ok)})
 
 
@@ -120,8 +124,9 @@ if __name__ == "__main__":
     ap.add_argument("--scale", type=float, default=1.0)
     a = ap.parse_args()
     if a.config == "c1":
-        c1()
+        res = c1()
     elif a.config == "c3":
-        c3(int(10000 * a.scale), int(500 * a.scale) or 1, 4000)
+        res = c3(int(10000 * a.scale), int(500 * a.scale) or 1, 4000)
     else:
-        c5(int(2000 * a.scale))
+        res = c5(int(2000 * a.scale))
+    print(json.dumps(res), flush=True)
