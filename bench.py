@@ -51,7 +51,7 @@ def parse_args():
     ap.add_argument("--length", type=int, default=int(os.environ.get("GKD_BENCH_LENGTH", "5000000")))
     ap.add_argument("--families", type=int, default=10)
     ap.add_argument("--k", type=int, default=21)
-    ap.add_argument("--panel", type=int, default=int(os.environ.get("GKD_BENCH_PANEL", "64")),
+    ap.add_argument("--panel", type=int, default=int(os.environ.get("GKD_BENCH_PANEL", "128")),
                     help="sets per exchanged panel (N>1)")
     ap.add_argument("--cpu-sample", type=int, default=int(os.environ.get("GKD_BENCH_CPU_SAMPLE", "24")))
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -263,7 +263,9 @@ def main():
         h_text.copy_(d_text)
     torch.cuda.synchronize()
 
-    eng = gkd.Engine(k=a.k, device=local)
+    # N>1: one build batch (= one set arena = one exchange panel) per `panel` genomes of the slice
+    ws = 0 if world == 1 else min(len(my_ids), a.panel) * Lg * 16 + (1 << 24)
+    eng = gkd.Engine(k=a.k, device=local, workspace_bytes=ws)
     ext = torch.cuda.ExternalStream(eng.stream_ptr, device=dev)
     inter = np.empty(total_pairs if world == 1 else 0, dtype=np.uint64)
     dist_out = np.empty(total_pairs if world == 1 else 0, dtype=np.float64)

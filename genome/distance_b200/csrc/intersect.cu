@@ -367,7 +367,7 @@ using BCfg7 = BucketCfg<3328, 1, 4, 8>;   // tmax 24, 32 warps per SM
 using BCfg8 = BucketCfg<5632, 1, 4, 4>;   // tmax 48 / 24, 16 warps per SM
 using BCfg9 = BucketCfg<5632, 1, 2, 9>;   // tmax 48 / 24, 18 warps per SM
 constexpr int N_BCFG = 10;
-constexpr int DEFAULT_BCFG = 3;
+constexpr int DEFAULT_BCFG = 9;
 static const uint32_t g_cfg_tmax32[N_BCFG] = {16, 16, 24, 24, 8, 8, 24, 24, 48, 48};
 
 #define GKD_FOR_EACH_BCFG(X) \

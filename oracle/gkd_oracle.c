@@ -491,12 +491,12 @@ typedef struct {
 } anyset;
 
 /* KmerType.createKmers(seq, K) */
-static int anyset_build(anyset *out, int mode, int alphabet, int k, const char *seq, size_t len) {
+static int anyset_build(anyset *out, int mode, int alphabet, int k, int ambig, const char *seq, size_t len) {
     out->mode = mode;
     out->s = NULL;
     out->i = NULL;
     if (mode == 0) {
-        out->s = orc_strset_new(alphabet, k, ORC_AMBIG_SKIP);
+        out->s = orc_strset_new(alphabet, k, ambig);
         if (!out->s || orc_strset_add(out->s, seq, len)) return -1;
     } else {
         out->i = orc_intset_new(alphabet, k);
@@ -538,7 +538,7 @@ typedef struct {
     const char *const *seqs;
     const size_t *lens;
     size_t n, b0;
-    int alphabet, k, batch, mode;
+    int alphabet, k, batch, mode, ambig;
     anyset *cache;
     uint64_t *inter;
     double *dist;
@@ -555,7 +555,7 @@ static void fd_row(long ii, void *arg) {
         int built = 0;
         if (j - job->b0 < (size_t)job->batch) other = &job->cache[j - job->b0]; /* :181-182 */
         else { /* :183-184 -- the set of an uncached column is rebuilt for every (row, column) */
-            if (anyset_build(&tmp, job->mode, job->alphabet, job->k, job->seqs[j], job->lens[j])) {
+            if (anyset_build(&tmp, job->mode, job->alphabet, job->k, job->ambig, job->seqs[j], job->lens[j])) {
                 anyset_free(&tmp);
                 __atomic_store_n(&job->rc, -1, __ATOMIC_RELAXED);
                 continue;
@@ -570,17 +570,18 @@ static void fd_row(long ii, void *arg) {
 }
 
 int orc_fasta_dist(const char *const *seqs, const size_t *lens, size_t n, int alphabet, int k,
-                   int batch, int threads, int mode, uint64_t *inter, double *dist) {
+                   int batch, int threads, int mode, int ambig, uint64_t *inter, double *dist) {
     if (batch < 1) return -1;
+    if (mode != 0 && ambig != ORC_AMBIG_SKIP) return -2; /* integer keys cannot hold literal k-mers */
     if (threads < 1) threads = orc_max_threads();
     anyset *cache = (anyset *)calloc((size_t)batch, sizeof(anyset));
     if (!cache) return -1;
-    fd_job job = {seqs, lens, n, 0, alphabet, k, batch, mode, cache, inter, dist, 0};
+    fd_job job = {seqs, lens, n, 0, alphabet, k, batch, mode, ambig, cache, inter, dist, 0};
     /* FastaDistanceProcessor.java:141 -- loop until the sequence list is empty */
     for (size_t b0 = 0; b0 < n && job.rc == 0; b0 += (size_t)batch) {
         size_t bsize = (n - b0 < (size_t)batch) ? n - b0 : (size_t)batch; /* :145-149 */
         for (size_t i = 0; i < bsize; i++)                                /* :151-155, serial */
-            if (anyset_build(&cache[i], mode, alphabet, k, seqs[b0 + i], lens[b0 + i])) job.rc = -1;
+            if (anyset_build(&cache[i], mode, alphabet, k, ambig, seqs[b0 + i], lens[b0 + i])) job.rc = -1;
         job.b0 = b0;
         if (job.rc == 0) parallel_for((long)bsize, threads, fd_row, &job); /* :157-158 */
         for (size_t i = 0; i < bsize; i++) anyset_free(&cache[i]);
@@ -602,19 +603,20 @@ static void qr_one(long i, void *arg) {
 }
 
 int orc_query_vs_ref(const char *const *q, const size_t *qlens, size_t nq, const char *const *r,
-                     const size_t *rlens, size_t nr, int alphabet, int k, int threads, int mode,
+                     const size_t *rlens, size_t nr, int alphabet, int k, int threads, int mode, int ambig,
                      uint64_t *inter, double *dist) {
+    if (mode != 0 && ambig != ORC_AMBIG_SKIP) return -2;
     if (threads < 1) threads = orc_max_threads();
     anyset *refs = (anyset *)calloc(nr ? nr : 1, sizeof(anyset));
     if (!refs) return -1;
     int rc = 0;
     /* GenomeProcessor.java:101-111 -- base genomes loaded serially, all resident */
     for (size_t i = 0; i < nr; i++)
-        if (anyset_build(&refs[i], mode, alphabet, k, r[i], rlens[i])) rc = -1;
+        if (anyset_build(&refs[i], mode, alphabet, k, ambig, r[i], rlens[i])) rc = -1;
     /* :129-147 -- one query at a time against all base genomes in parallel */
     for (size_t qi = 0; qi < nq && rc == 0; qi++) {
         anyset qs;
-        if (anyset_build(&qs, mode, alphabet, k, q[qi], qlens[qi])) {
+        if (anyset_build(&qs, mode, alphabet, k, ambig, q[qi], qlens[qi])) {
             anyset_free(&qs);
             rc = -1;
             break;

@@ -86,13 +86,14 @@ int orc_double_to_string(double v, char *buf, size_t cap);
 /* FastaDistanceProcessor.runReporter (:134-165) + computePairs (:174-194): all pairs i<j of n
  * records, batch-cached sets, uncached columns rebuilt per (row, column), rows in parallel.
  * inter/dist are row-major strict upper triangle, length n*(n-1)/2.  mode: 0 = STRING, 1 = INTEGER.
- * Returns 0, or -1 on allocation failure. */
+ * ambig = ORC_AMBIG_* (the literal policy exists in STRING mode only).
+ * Returns 0, -1 on allocation failure, -2 for INTEGER mode with the literal policy. */
 int orc_fasta_dist(const char *const *seqs, const size_t *lens, size_t n, int alphabet, int k,
-                   int batch, int threads, int mode, uint64_t *inter, double *dist);
+                   int batch, int threads, int mode, int ambig, uint64_t *inter, double *dist);
 /* GenomeProcessor.runReporter (:119-150): every query against every base genome; one record per
  * genome here (multi-contig genomes go through the set API).  inter/dist are nq*nr row-major. */
 int orc_query_vs_ref(const char *const *q, const size_t *qlens, size_t nq, const char *const *r,
-                     const size_t *rlens, size_t nr, int alphabet, int k, int threads, int mode,
+                     const size_t *rlens, size_t nr, int alphabet, int k, int threads, int mode, int ambig,
                      uint64_t *inter, double *dist);
 int orc_max_threads(void);
 

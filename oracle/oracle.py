@@ -67,10 +67,10 @@ def lib() -> C.CDLL:
     L.orc_distance.restype = dbl
     L.orc_distance.argtypes = [u64, u64, u64]
     L.orc_double_to_string.argtypes = [dbl, C.c_char_p, sz]
-    L.orc_fasta_dist.argtypes = [C.POINTER(C.c_char_p), C.POINTER(sz), sz, i32, i32, i32, i32, i32,
+    L.orc_fasta_dist.argtypes = [C.POINTER(C.c_char_p), C.POINTER(sz), sz, i32, i32, i32, i32, i32, i32,
                                  C.POINTER(u64), C.POINTER(dbl)]
     L.orc_query_vs_ref.argtypes = [C.POINTER(C.c_char_p), C.POINTER(sz), sz, C.POINTER(C.c_char_p),
-                                   C.POINTER(sz), sz, i32, i32, i32, i32, C.POINTER(u64), C.POINTER(dbl)]
+                                   C.POINTER(sz), sz, i32, i32, i32, i32, i32, C.POINTER(u64), C.POINTER(dbl)]
     L.orc_max_threads.restype = i32
     _lib = L
     return L
@@ -173,28 +173,30 @@ def _cstr_array(seqs: Sequence):
     return bs, arr, lens
 
 
-def fasta_dist(seqs: Sequence, k: int, alphabet: int = DNA, batch: int = 20, threads: int = 0, mode: int = 0):
+def fasta_dist(seqs: Sequence, k: int, alphabet: int = DNA, batch: int = 20, threads: int = 0, mode: int = 0,
+               ambig: int = AMBIG_SKIP):
     """FastaDistanceProcessor restatement: (inter, dist) over the strict upper triangle, row-major."""
     n = len(seqs)
     npairs = n * (n - 1) // 2
     keep, arr, lens = _cstr_array(seqs)
     inter = np.zeros(max(npairs, 1), dtype=np.uint64)
     dist = np.zeros(max(npairs, 1), dtype=np.float64)
-    rc = lib().orc_fasta_dist(arr, lens, n, alphabet, k, batch, threads, mode,
+    rc = lib().orc_fasta_dist(arr, lens, n, alphabet, k, batch, threads, mode, ambig,
                               inter.ctypes.data_as(C.POINTER(C.c_uint64)), dist.ctypes.data_as(C.POINTER(C.c_double)))
     if rc:
         raise MemoryError("oracle fasta_dist failed")
     return inter[:npairs], dist[:npairs]
 
 
-def query_vs_ref(queries: Sequence, refs: Sequence, k: int, alphabet: int = DNA, threads: int = 0, mode: int = 0):
+def query_vs_ref(queries: Sequence, refs: Sequence, k: int, alphabet: int = DNA, threads: int = 0, mode: int = 0,
+                 ambig: int = AMBIG_SKIP):
     """GenomeProcessor restatement: (inter, dist) as (nq, nr) arrays."""
     kq, qa, ql = _cstr_array(queries)
     kr, ra, rl = _cstr_array(refs)
     nq, nr = len(queries), len(refs)
     inter = np.zeros(max(nq * nr, 1), dtype=np.uint64)
     dist = np.zeros(max(nq * nr, 1), dtype=np.float64)
-    rc = lib().orc_query_vs_ref(qa, ql, nq, ra, rl, nr, alphabet, k, threads, mode,
+    rc = lib().orc_query_vs_ref(qa, ql, nq, ra, rl, nr, alphabet, k, threads, mode, ambig,
                                 inter.ctypes.data_as(C.POINTER(C.c_uint64)), dist.ctypes.data_as(C.POINTER(C.c_double)))
     if rc:
         raise MemoryError("oracle query_vs_ref failed")

@@ -105,3 +105,25 @@ def test_bad_config_is_einval_or_ecuda():
         with pytest.raises(gkd.GkdError) as e:
             gkd.Engine(**kw)
         assert e.value.code == _lib.GKD_EINVAL
+
+
+def test_jni_glue_compiles_and_matches_the_java_declarations(tmp_path):
+    """No JDK in the image: java/jni/gkd_jni.c is compiled against a stub jni.h (types and the JNIEnv members
+    it uses) with -Wall -Wextra -Werror, linked against libgkd.so, and must define exactly one JNI function
+    per `static native` method declared in GkdNative.java."""
+    import subprocess
+
+    so = tmp_path / "libgkd_jni.so"
+    subprocess.check_call(["gcc", "-std=c11", "-Wall", "-Wextra", "-Werror", "-fPIC", "-shared",
+                           "-I", os.path.join(ROOT, "tests", "stubs"), "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "java", "jni", "gkd_jni.c"), "-L", os.path.dirname(_lib.LIB_PATH), "-lgkd",
+                           "-o", str(so)])
+    syms = subprocess.check_output(["nm", "-D", "--defined-only", str(so)]).decode()
+    defined = set(re.findall(r"Java_org_theseed_sequence_gpu_GkdNative_(\w+)", syms))
+    with open(os.path.join(ROOT, "java", "org", "theseed", "sequence", "gpu", "GkdNative.java")) as f:
+        declared = set(re.findall(r"static native [\w\[\]]+ (\w+)\(", f.read()))
+    assert declared and declared == defined, declared ^ defined
+    # the engine class calls only natives that exist
+    with open(os.path.join(ROOT, "java", "org", "theseed", "sequence", "gpu", "GpuKmerEngine.java")) as f:
+        used = set(re.findall(r"GkdNative\.(\w+)\(", f.read()))
+    assert used <= declared, used - declared

@@ -513,3 +513,70 @@ def test_packed_sets_are_adopted_in_place(orc):
             with pytest.raises(gkd.GkdError) as err:
                 f.adopt_sets(bufs[0], bad)
             assert err.value.code == -1
+
+
+def test_literal_ambiguity_policy(orc):
+    """GKD_AMBIG_LITERAL against the oracle's literal string sets (both policies are explicit switches: the
+    reference does not pin what DnaKmers does with non-acgt characters).  Host strings, numpy and device
+    inputs, multi-contig genomes, RNA, odd and even K, and the explicit-pair and rectangular calls."""
+    import torch
+
+    rng = random.Random(4242)
+    base = _rand_dna(rng, 3000)
+    genomes = []
+    for g in range(6):
+        s = list(_mutate(rng, base, 0.01 * g))
+        for _ in range(2 + g):
+            p = rng.randrange(len(s))
+            run = rng.choice([1, 3, 25, 60])
+            s[p:p + run] = rng.choice(["n", "N", "R", "y", "-", "x"]) * run
+        s = "".join(s)
+        genomes.append([s[:1700], s[1700:]] if g % 2 else [s])
+    genomes.append([base])                       # no ambiguity at all
+    genomes.append(["nnnnnnnnnnnnnnnnnnnnnnnnnnnnnnnnnnnnnnnn"])  # nothing but ambiguity
+    genomes.append(["acgtn"])                     # shorter than most K
+    for k in (4, 9, 21, 22):
+        ssets = [orc.StrSet(g, k, orc.DNA, orc.AMBIG_LITERAL) for g in genomes]
+        with gkd.Engine(k=k, ambig_policy=gkd.AMBIG_LITERAL) as e:
+            for i, g in enumerate(genomes):
+                if i == 2:    # device text
+                    e.add([torch.tensor(list(c.encode()), dtype=torch.uint8, device="cuda") for c in g])
+                elif i == 3:  # numpy text
+                    e.add([np.frombuffer(c.encode(), dtype=np.uint8) for c in g])
+                else:
+                    e.add(g)
+            e.build()
+            assert [e.set_size(i)[0] for i in range(len(genomes))] == [len(s) for s in ssets], k
+            gi, gd = e.all_vs_all()
+            t = 0
+            for i in range(len(genomes)):
+                for j in range(i + 1, len(genomes)):
+                    I = ssets[i].similarity(ssets[j])
+                    assert int(gi[t]) == I and gd[t] == orc.distance(I, len(ssets[i]), len(ssets[j])), (k, i, j)
+                    t += 1
+            qi, qd = e.query_vs_ref([0, 1, 7], [2, 7, 6])
+            assert int(qi[0, 0]) == ssets[0].similarity(ssets[2]) and qd[2, 1] == 0.0
+            inter, dist, ca, cb = e.pairs_ex([0, 7], [1, 7])
+            assert ca[0] == int(inter[0]) / len(ssets[0]) and cb[1] == 1.0
+            with pytest.raises(gkd.GkdError):  # literal k-mers live on the host: not exchanged
+                e.describe_sets(0, 1)
+        # the default policy on the same input drops those k-mers
+        with gkd.Engine(k=k) as e:
+            e.add(genomes[0])
+            e.build()
+            assert e.set_size(0)[0] == len(orc.StrSet(genomes[0], k, orc.DNA, orc.AMBIG_SKIP)) < len(ssets[0])
+    s = _rand_dna(rng, 500, "acgun")
+    with gkd.Engine(k=7, alphabet=gkd.RNA, ambig_policy=gkd.AMBIG_LITERAL) as e:
+        e.add(s)
+        e.add(s.replace("u", "t"))
+        e.build()
+        assert e.set_size(0)[0] == len(orc.StrSet(s, 7, orc.RNA, orc.AMBIG_LITERAL)) and e.pair(0, 1)[2] == 0.0
+    # the command restatement with the literal policy (oracle string mode) against the engine
+    seqs = ["".join(c) for c in genomes[:6]]
+    oi, od = orc.fasta_dist(seqs, 21, batch=2, threads=0, mode=0, ambig=orc.AMBIG_LITERAL)
+    with gkd.Engine(k=21, ambig_policy=gkd.AMBIG_LITERAL) as e:
+        for x in seqs:
+            e.add(x)
+        e.build()
+        gi, gd = e.all_vs_all()
+    assert np.array_equal(gi, oi) and np.array_equal(gd, od)

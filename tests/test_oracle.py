@@ -176,3 +176,53 @@ def test_fasta_dist_command_restatement(orc):
 def test_parse_fasta(orc):
     recs = orc.parse_fasta(">s1 first one\nACGT\nAC\n\n>s2\nGG\r\n>s3   spaced  comment \n")
     assert recs == [("s1", "first one", "ACGTAC"), ("s2", "", "GG"), ("s3", "spaced  comment", "")]
+
+
+def test_literal_ambiguity_policy_restatements_agree(orc):
+    """ORC_AMBIG_LITERAL (recalled upstream behaviour, unpinned): windows with a character outside acgt stay
+    in the set as literal strings and so do their reverse-complement windows (unknown base -> 'n').  The C
+    string set, the command restatement and the literal Python sets must agree; SKIP differs when N occurs."""
+    import random
+
+    rng = random.Random(99)
+    seqs = []
+    base = "".join(rng.choice("acgt") for _ in range(600))
+    for g in range(5):
+        s = list(base)
+        for _ in range(3 + g):
+            p = rng.randrange(len(s))
+            run = rng.choice([1, 2, 7, 30])
+            s[p:p + run] = rng.choice(["n", "N", "r", "y", "-"]) * run
+        seqs.append("".join(s))
+    seqs.append(base)
+    for k in (5, 8, 21):
+        psets = [orc.py_kmer_set(s, k, orc.DNA, orc.AMBIG_LITERAL) for s in seqs]
+        ssets = [orc.StrSet(s, k, orc.DNA, orc.AMBIG_LITERAL) for s in seqs]
+        assert [len(x) for x in ssets] == [len(x) for x in psets]
+        inter, dist = orc.fasta_dist(seqs, k, batch=3, threads=2, mode=0, ambig=orc.AMBIG_LITERAL)
+        t = 0
+        for i in range(len(seqs)):
+            for j in range(i + 1, len(seqs)):
+                want = orc.py_distance(psets[i], psets[j])
+                assert (int(inter[t]), dist[t]) == want
+                assert ssets[i].similarity(ssets[j]) == want[0]
+                t += 1
+        skip = orc.StrSet(seqs[0], k, orc.DNA, orc.AMBIG_SKIP)
+        assert len(skip) < len(ssets[0])
+        assert len(orc.StrSet(base, k, orc.DNA, orc.AMBIG_LITERAL)) == len(orc.StrSet(base, k, orc.DNA, orc.AMBIG_SKIP))
+    with pytest.raises(MemoryError):
+        orc.fasta_dist(seqs, 5, mode=1, ambig=orc.AMBIG_LITERAL)  # integer keys cannot hold literal k-mers
+
+
+def test_numpy_generator_port_matches_the_engine_generator():
+    """oracle/synth.py (what the CPU arm of bench.py uses) is byte-identical to gkd_synth_* (host path)"""
+    import numpy as np
+
+    import genome.distance_b200 as gkd
+    from oracle import synth as osynth
+
+    for protein in (False, True):
+        for fam, mem, rate in ((0, 0, 0.0), (2, 5, 0.05), (7, 1, 0.2), (1, 3, 0.001)):
+            a = np.empty(50021, dtype=np.uint8)
+            gkd.synth(a, 0x5EED0000, fam, mem, rate, protein=protein)
+            assert np.array_equal(a, osynth.synth(50021, 0x5EED0000, fam, mem, rate, protein=protein, chunk=7000))
