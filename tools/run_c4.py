@@ -81,8 +81,8 @@ def main():
         agg["inter_sum"] += int(inter.sum(dtype=np.uint64))
         agg["dist_sum"] += float(d.sum())
         agg["related"] += int((d < 1.0).sum())
-        # Poisson thinning keeps ~per_rank_check pairs overall, plus every related pair has double weight
-        k = rng.binomial(inter.size, min(1.0, 1.5 * per_rank_check / my_pairs_expected))
+        # binomial thinning keeps ~2x per_rank_check pairs overall, uniformly over this rank's pairs
+        k = rng.binomial(inter.size, min(1.0, 2.0 * per_rank_check / my_pairs_expected))
         if k:
             idx = rng.choice(inter.size, size=k, replace=False)
             gi, gj = np.asarray(gi).reshape(-1), np.asarray(gj).reshape(-1)
@@ -91,6 +91,7 @@ def main():
 
     stats = {}
     sharding.ring_all_vs_all(eng, n, world, rank, dev, panel_genomes=a.panel, sink=sink, stats=stats)
+    rng.shuffle(sample)
     torch.cuda.synchronize()
     t_mine = time.perf_counter() - t1
     m = eng.metrics()
@@ -102,9 +103,7 @@ def main():
 
     # parity: recompute sampled pairs from the seeds in a fresh context (different build batch, two-set
     # all-vs-all instead of a rectangular block) and compare bit for bit
-    related = [s for s in sample if s[3] < 1.0]
-    others = [s for s in sample if s[3] >= 1.0]
-    chosen = (related[: per_rank_check // 2] + others)[:per_rank_check]
+    chosen = sample[:per_rank_check]  # already a uniform random sample of this rank's pairs
     bad = 0
     t3 = time.perf_counter()
     with gkd.Engine(k=21, device=local) as chk:
