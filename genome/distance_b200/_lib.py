@@ -12,6 +12,7 @@ GKD_OK, GKD_EINVAL, GKD_EIO, GKD_ENOMEM, GKD_ECUDA, GKD_ESTATE = 0, -1, -2, -3, 
 DNA, PROT, RNA = 0, 1, 2
 STRAND_BOTH, STRAND_CANONICAL = 0, 1
 AMBIG_SKIP, AMBIG_LITERAL = 0, 1
+HASH_JAVA_STRING, HASH_MURMUR3 = 0, 1
 ABI_VERSION = 2
 
 
@@ -75,6 +76,8 @@ SYMBOLS = {
     "gkd_query_vs_ref_ex": (_i32, [_vp, _vp, _u32, _vp, _u32, C.POINTER(GkdOutputs)]),
     "gkd_pairs_ex": (_i32, [_vp, _vp, _vp, _u64, C.POINTER(GkdOutputs)]),
     "gkd_pair": (_i32, [_vp, _u32, _u32, _pu64, _pu64, _pdbl]),
+    "gkd_hash_set": (_i32, [_vp, _u32, _u32, _i32, _vp, _pu32]),
+    "gkd_sketch_distances": (_i32, [_vp, _u32, _i32, _vp, _vp, _u64, _vp]),
     "gkd_format_double": (_i32, [_dbl, C.c_char_p, C.c_size_t]),
     "gkd_get_metrics": (_i32, [_vp, C.POINTER(GkdMetrics)]),
     "gkd_stream": (_vp, [_vp]),

@@ -111,6 +111,7 @@ struct gkd_ctx {
 
     DevBuf keys_a, keys_b, tile_hist, tile_uniq, genome_counts, batch_genomes, set_build;
     DevBuf d_sets, counts, pal_counts, d_inter, d_dist, d_ca, d_cb, ids_a, ids_b, work_counter;
+    DevBuf sk_cand, sk_misc, sk_sig, sk_len, sk_out;
     bool sets_dirty = true;
 
     std::unordered_map<std::string, uint32_t> lit_dict;  // GKD_AMBIG_LITERAL: literal k-mer -> dense id
@@ -762,7 +763,7 @@ int run_pairs(gkd_ctx *c, const HostPairs &hp, const gkd_outputs &out) {
         L = std::min(L, lmax);
         const uint64_t max_groups = ((1ull << L) + 31) >> 5;
         uint64_t gpi;
-        if (one_item) gpi = max_groups;
+        if (one_item || max_groups <= 64) gpi = max_groups;  // tiny sets: a pair is one item (the per-item set-up would dominate)
         else if (c->cfg.segment_keys) gpi = std::max<uint64_t>(1, c->cfg.segment_keys / (64ull * p.tmax));
         else {
             const uint64_t warps = (uint64_t)c->n_sms * intersect_warps_per_sm(c->low_bits);
@@ -964,6 +965,7 @@ int gkd_create(gkd_ctx **out, const gkd_config *cfg) {
     // function attributes are per device: every context sets them for its own device
     CK_CREATE(intersect_configure());
     CK_CREATE(sort_configure());
+    CK_CREATE(sketch_configure());
 #undef CK_CREATE
     *out = c;
     return GKD_OK;
@@ -1033,7 +1035,8 @@ int gkd_destroy(gkd_ctx *c) {
     for (auto &s : c->slabs) cudaFreeAsync(s.base, c->stream);
     DevBuf *bufs[] = {&c->keys_a, &c->keys_b, &c->tile_hist, &c->tile_uniq, &c->genome_counts, &c->batch_genomes,
                       &c->set_build, &c->d_sets, &c->counts, &c->pal_counts, &c->d_inter, &c->d_dist, &c->d_ca,
-                      &c->d_cb, &c->ids_a, &c->ids_b, &c->work_counter};
+                      &c->d_cb, &c->ids_a, &c->ids_b, &c->work_counter, &c->sk_cand, &c->sk_misc, &c->sk_sig,
+                      &c->sk_len, &c->sk_out};
     for (DevBuf *b : bufs)
         if (b->p) cudaFreeAsync(b->p, c->stream);
     cudaStreamSynchronize(c->stream);
@@ -1493,6 +1496,112 @@ int gkd_pair(gkd_ctx *c, uint32_t a, uint32_t b, uint64_t *inter, uint64_t *uni,
         *uni = sa + sb - I;
     }
     return GKD_OK;
+}
+
+// ---- MinHash sketches ---------------------------------------------------------------------------------------
+// hashSet(width) of one set into device memory `d_out` (width int32 slots); *n_out = entries written
+static int sketch_one(gkd_ctx *c, uint32_t id, uint32_t width, int hash, int32_t *d_out, uint32_t *n_out) {
+    const GenomeRec &g = c->genomes[id];
+    const bool nuc = c->cfg.alphabet != GKD_PROT;
+    const int both = nuc && c->cfg.strand_mode == GKD_STRAND_BOTH;
+    if (!g.lit.empty()) return fail(c, GKD_EINVAL, "sketches of sets with literal ambiguous k-mers are not supported");
+    int rc;
+    if ((rc = ensure(c, c->sk_cand, (uint64_t)SKETCH_CAP * 4))) return rc;
+    if ((rc = ensure(c, c->sk_misc, 16))) return rc;
+    uint32_t *misc = (uint32_t *)c->sk_misc.p;  // [0] candidates seen, [1] entries written, [2] distinct candidates
+    const uint64_t n_codes = (uint64_t)g.desc.main.n * (both ? 2 : 1);
+    // codes are close to uniform over 2^32: keep about 2*width+64 of them; everything when the set is small
+    const uint64_t want = 2ull * width + 64;
+    uint64_t thresh = n_codes <= SKETCH_CAP / 2 ? 0xFFFFFFFFull : std::min<uint64_t>(0xFFFFFFFFull, (want << 32) / n_codes);
+    for (int attempt = 0; attempt < 40; attempt++) {
+        CK(launch_sketch_filter(g.desc.main, c->mix, c->low_bits, c->cfg.alphabet, c->k, both, hash, (uint32_t)thresh,
+                                (uint32_t *)c->sk_cand.p, SKETCH_CAP, misc, c->stream));
+        uint32_t seen = 0;
+        CK(cudaMemcpyAsync(&seen, misc, 4, cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        c->m.launches++;
+        if (seen > SKETCH_CAP) {  // too many below the threshold (skewed codes): tighten
+            thresh /= 4;
+            continue;
+        }
+        CK(launch_sketch_finish((const uint32_t *)c->sk_cand.p, seen, width, d_out, misc + 1, misc + 2, c->stream));
+        uint32_t res[2] = {0, 0};
+        CK(cudaMemcpyAsync(res, misc + 1, 8, cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        c->m.launches++;
+        if (res[1] >= width || thresh >= 0xFFFFFFFFull) {  // enough distinct codes, or every code was considered
+            *n_out = res[0];
+            return GKD_OK;
+        }
+        thresh = std::min<uint64_t>(0xFFFFFFFFull, thresh * 4 + 1024);  // too few distinct codes: widen
+    }
+    return fail(c, GKD_EINVAL, "sketch threshold search did not converge for set %u", id);
+}
+
+int gkd_hash_set(gkd_ctx *c, uint32_t id, uint32_t width, int hash, int32_t *out, uint32_t *n_out) {
+    CHECK_CTX(c);
+    int rc = check_built(c, id);
+    if (rc) return rc;
+    if (width == 0 || width > SKETCH_MAX_WIDTH) return fail(c, GKD_EINVAL, "sketch width must be 1..%u", SKETCH_MAX_WIDTH);
+    if (hash != GKD_HASH_JAVA_STRING && hash != GKD_HASH_MURMUR3) return fail(c, GKD_EINVAL, "unknown sketch hash %d", hash);
+    if (!out || !n_out) return fail(c, GKD_EINVAL, "gkd_hash_set: null output");
+    CK(cudaSetDevice(c->cfg.device));
+    if ((rc = ensure(c, c->sk_out, (uint64_t)SKETCH_MAX_WIDTH * 4))) return rc;
+    uint32_t n = 0;
+    if ((rc = sketch_one(c, id, width, hash, (int32_t *)c->sk_out.p, &n))) return rc;
+    if (n) CK(cudaMemcpyAsync(out, c->sk_out.p, (uint64_t)n * 4, cudaMemcpyDefault, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    c->m.d2h_bytes += (uint64_t)n * 4;
+    *n_out = n;
+    return GKD_OK;
+}
+
+int gkd_sketch_distances(gkd_ctx *c, uint32_t width, int hash, const uint32_t *a, const uint32_t *b, uint64_t n_pairs,
+                         double *dist) {
+    CHECK_CTX(c);
+    if (width == 0 || width > SKETCH_MAX_WIDTH) return fail(c, GKD_EINVAL, "sketch width must be 1..%u", SKETCH_MAX_WIDTH);
+    if (hash != GKD_HASH_JAVA_STRING && hash != GKD_HASH_MURMUR3) return fail(c, GKD_EINVAL, "unknown sketch hash %d", hash);
+    if (n_pairs == 0) return GKD_OK;
+    if (!a || !b || !dist) return fail(c, GKD_EINVAL, "gkd_sketch_distances: null argument");
+    if (n_pairs > 0xFFFFFFFFull) return fail(c, GKD_EINVAL, "gkd_sketch_distances: more than 2^32 pairs in one call");
+    CK(cudaSetDevice(c->cfg.device));
+    ABI_GUARD_BEGIN
+    // sketch every set that occurs in the list once, into a dense signature matrix
+    const uint32_t n_sets = (uint32_t)c->genomes.size();
+    std::vector<uint32_t> slot(n_sets, UINT32_MAX), order;
+    std::vector<uint32_t> ra(n_pairs), rb(n_pairs);
+    for (uint64_t t = 0; t < n_pairs; t++) {
+        for (uint32_t id : {a[t], b[t]}) {
+            int rc = check_built(c, id);
+            if (rc) return rc;
+            if (slot[id] == UINT32_MAX) {
+                slot[id] = (uint32_t)order.size();
+                order.push_back(id);
+            }
+        }
+        ra[t] = slot[a[t]];
+        rb[t] = slot[b[t]];
+    }
+    int rc;
+    if ((rc = ensure(c, c->sk_sig, (uint64_t)order.size() * width * 4))) return rc;
+    if ((rc = ensure(c, c->sk_len, (uint64_t)order.size() * 4))) return rc;
+    std::vector<uint32_t> lens(order.size());
+    for (size_t s = 0; s < order.size(); s++)
+        if ((rc = sketch_one(c, order[s], width, hash, (int32_t *)c->sk_sig.p + s * width, &lens[s]))) return rc;
+    if ((rc = ensure(c, c->ids_a, n_pairs * 4))) return rc;
+    if ((rc = ensure(c, c->ids_b, n_pairs * 4))) return rc;
+    if ((rc = ensure(c, c->d_dist, n_pairs * 8))) return rc;
+    CK(cudaMemcpyAsync(c->sk_len.p, lens.data(), lens.size() * 4, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(c->ids_a.p, ra.data(), n_pairs * 4, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(c->ids_b.p, rb.data(), n_pairs * 4, cudaMemcpyHostToDevice, c->stream));
+    CK(launch_sketch_distance((const int32_t *)c->sk_sig.p, (const uint32_t *)c->sk_len.p, width, (const uint32_t *)c->ids_a.p,
+                              (const uint32_t *)c->ids_b.p, n_pairs, (double *)c->d_dist.p, c->stream));
+    c->m.launches++;
+    CK(cudaMemcpyAsync(dist, c->d_dist.p, n_pairs * 8, cudaMemcpyDefault, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    c->m.d2h_bytes += n_pairs * 8;
+    return GKD_OK;
+    ABI_GUARD_END(c)
 }
 
 int gkd_get_metrics(const gkd_ctx *c, gkd_metrics *out) {

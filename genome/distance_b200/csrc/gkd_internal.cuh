@@ -221,6 +221,16 @@ struct EpilogueOut {
 };
 cudaError_t launch_epilogue(const SetDesc *sets, PairSource src, const uint32_t *counts, const uint32_t *pal_counts,
                             int both_strands, EpilogueOut out, cudaStream_t s);
+// MinHash sketches (sketch.cu)
+constexpr uint32_t SKETCH_CAP = 32768;        // candidate codes one CTA sorts in shared memory
+constexpr uint32_t SKETCH_MAX_WIDTH = 4096;   // widest signature (the reference's commands use 360 and 2000)
+cudaError_t sketch_configure();
+cudaError_t launch_sketch_filter(SubSet set, MixParams mix, int low_bits, int alphabet, int k, int both, int kind,
+                                 uint32_t thresh, uint32_t *cand, uint32_t cap, uint32_t *n_cand, cudaStream_t s);
+cudaError_t launch_sketch_finish(const uint32_t *cand, uint32_t n, uint32_t width, int32_t *out, uint32_t *n_out,
+                                 uint32_t *n_distinct, cudaStream_t s);
+cudaError_t launch_sketch_distance(const int32_t *sig, const uint32_t *len, uint32_t width, const uint32_t *a,
+                                   const uint32_t *b, uint64_t n_pairs, double *dist, cudaStream_t s);
 // synthetic data
 cudaError_t launch_synth(char *dst, uint64_t len, uint64_t seed, uint32_t family, uint32_t member, double rate,
                          int protein, cudaStream_t s);

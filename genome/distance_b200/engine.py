@@ -268,6 +268,22 @@ class Engine:
         self._ck(self._L.gkd_pairs_ex(self._h, aa.ctypes.data, ba.ctypes.data, n, C.byref(o)))
         return inter, dist, ca, cb
 
+    # -- MinHash sketches --------------------------------------------------------------------------
+    def hash_set(self, i: int, width: int, hash_kind: int = 0) -> np.ndarray:
+        """SequenceKmers.hashSet(width): the smallest distinct hash codes of set i, ascending, as int32"""
+        out = np.empty(width, dtype=np.int32)
+        n = C.c_uint32()
+        self._ck(self._L.gkd_hash_set(self._h, i, width, hash_kind, out.ctypes.data, C.byref(n)))
+        return out[: n.value].copy()
+
+    def sketch_distances(self, width: int, a: Sequence[int], b: Sequence[int], hash_kind: int = 0) -> np.ndarray:
+        """Sketch.distance for a pair list (sketches built and compared on the device)"""
+        aa, ba = np.ascontiguousarray(a, dtype=np.uint32), np.ascontiguousarray(b, dtype=np.uint32)
+        dist = np.empty(aa.size, dtype=np.float64)
+        self._ck(self._L.gkd_sketch_distances(self._h, width, hash_kind, aa.ctypes.data, ba.ctypes.data, aa.size,
+                                              dist.ctypes.data))
+        return dist
+
     def pair(self, a: int, b: int) -> Tuple[int, int, float]:
         i, u, d = C.c_uint64(), C.c_uint64(), C.c_double()
         self._ck(self._L.gkd_pair(self._h, a, b, C.byref(i), C.byref(u), C.byref(d)))

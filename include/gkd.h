@@ -209,6 +209,22 @@ int gkd_pairs_ex(gkd_ctx *ctx, const uint32_t *a, const uint32_t *b, uint64_t n_
  * FastaDistanceRepsProcessor.java:128); uni = |A|+|B|-I */
 int gkd_pair(gkd_ctx *ctx, uint32_t a, uint32_t b, uint64_t *inter, uint64_t *uni, double *dist);
 
+/* ---- MinHash sketches ---------------------------------------------------------
+ * SequenceKmers.hashSet(width) and Sketch.distance (SketchProcessor.java:91, WidthProcessor.java:177-183,
+ * MashProcessor.java:116-150).  The implementing classes are external and the hash they use is NOT pinned by
+ * the reference tree, so it is a switch: java.lang.String.hashCode of the k-mer string, or murmur3_x86_32
+ * (seed 0) of its bytes (build.xml:30 ships a murmur3 jar next to the sequence module). */
+typedef enum gkd_sketch_hash { GKD_HASH_JAVA_STRING = 0, GKD_HASH_MURMUR3 = 1 } gkd_sketch_hash;
+/* hashSet(width): the `width` (<= 4096) smallest distinct hash codes of the set's k-mer strings (both strands
+ * for nucleotide sets under GKD_STRAND_BOTH), ascending as signed Java ints; *n_out <= width entries are
+ * written to out (fewer when the set has fewer distinct codes). */
+int gkd_hash_set(gkd_ctx *ctx, uint32_t id, uint32_t width, int hash, int32_t *out, uint32_t *n_out);
+/* Sketch.distance for a pair list: the sketches of the sets involved are built (hashSet(width)) and compared
+ * on the device with the bottom-w estimator: over the w = min(|A|,|B|) smallest codes of the union, m are in
+ * both; distance = 1 - m / w (1.0 for an empty signature). */
+int gkd_sketch_distances(gkd_ctx *ctx, uint32_t width, int hash, const uint32_t *a, const uint32_t *b, uint64_t n_pairs,
+                         double *dist);
+
 /* ---- text + metrics --------------------------------------------------------------------------- */
 /* java.lang.Double.toString layout ("" + distance, FastaDistanceProcessor.java:189-190,
  * GenomeProcessor.java:144); returns the length written, excluding the NUL */

@@ -20,7 +20,7 @@ import org.theseed.sequence.SequenceKmers;
 
 /**
  * GPU replacement body for the "genomes" command (reference: GenomeProcessor.java).  Register it in App.java
- * in place of GenomeProcessor.
+ * in place of GenomeProcessor (case "genomes", App.java:52-54).
  *
  * Unchanged on purpose: options (-K/--kmerSize/--kmer default 21, -m/--maxDist default 0.9 -- validated and,
  * exactly as in the reference (:143-146), never applied --, -t/--type default DIR), validation messages, the

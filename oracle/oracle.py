@@ -269,3 +269,83 @@ def parse_fasta(text: str) -> List[Tuple[str, str, str]]:
     if label is not None:
         recs.append((label, comment, "".join(chunks)))
     return recs
+
+
+# ------------------------------------------------------------------------------------------------
+# MinHash sketches.  UNPINNED: SequenceKmers.hashSet / Sketch.distance live in the external
+# org.theseed.sequence module; restated here as "the `width` smallest distinct hash codes of the set's k-mer
+# strings, ascending as Java ints" and the bottom-w estimator, with the string hash as a switch
+# (call sites: SketchProcessor.java:91, WidthProcessor.java:177-183, MashProcessor.java:116-150).
+# ------------------------------------------------------------------------------------------------
+HASH_JAVA_STRING, HASH_MURMUR3 = 0, 1
+
+
+def _s32(x: int) -> int:
+    x &= 0xFFFFFFFF
+    return x - (1 << 32) if x & 0x80000000 else x
+
+
+def java_string_hash(s) -> int:
+    """java.lang.String.hashCode of a Latin-1 string, as a signed 32-bit int"""
+    h = 0
+    for ch in (s.encode("latin-1") if isinstance(s, str) else s):
+        h = (31 * h + ch) & 0xFFFFFFFF
+    return _s32(h)
+
+
+def murmur3_32(data, seed: int = 0) -> int:
+    """murmur3_x86_32 of the bytes, as a signed 32-bit int"""
+    data = data.encode("latin-1") if isinstance(data, str) else bytes(data)
+    c1, c2, h, n = 0xCC9E2D51, 0x1B873593, seed & 0xFFFFFFFF, len(data)
+
+    def rotl(x, r):
+        return ((x << r) | (x >> (32 - r))) & 0xFFFFFFFF
+
+    for i in range(0, n - n % 4, 4):
+        k = int.from_bytes(data[i:i + 4], "little")
+        k = (k * c1) & 0xFFFFFFFF
+        k = rotl(k, 15)
+        k = (k * c2) & 0xFFFFFFFF
+        h ^= k
+        h = rotl(h, 13)
+        h = (h * 5 + 0xE6546B64) & 0xFFFFFFFF
+    tail = data[n - n % 4:]
+    k = 0
+    if len(tail) >= 3:
+        k ^= tail[2] << 16
+    if len(tail) >= 2:
+        k ^= tail[1] << 8
+    if len(tail) >= 1:
+        k ^= tail[0]
+        k = (k * c1) & 0xFFFFFFFF
+        k = rotl(k, 15)
+        k = (k * c2) & 0xFFFFFFFF
+        h ^= k
+    h ^= n
+    h ^= h >> 16
+    h = (h * 0x85EBCA6B) & 0xFFFFFFFF
+    h ^= h >> 13
+    h = (h * 0xC2B2AE35) & 0xFFFFFFFF
+    h ^= h >> 16
+    return _s32(h)
+
+
+def py_hash_set(kmers: set, width: int, kind: int = HASH_JAVA_STRING) -> List[int]:
+    """SequenceKmers.hashSet(width) over a literal k-mer string set (py_kmer_set)"""
+    fn = java_string_hash if kind == HASH_JAVA_STRING else murmur3_32
+    return sorted({fn(k) for k in kmers})[:width]
+
+
+def py_sketch_distance(a: Sequence[int], b: Sequence[int]) -> float:
+    """Sketch.distance: over the w = min(|a|,|b|) smallest codes of the union, m are in both; 1 - m/w"""
+    w = min(len(a), len(b))
+    if w == 0:
+        return 1.0
+    i = j = m = 0
+    for _ in range(w):
+        x, y = a[i], b[j]
+        m += x == y
+        i, j = i + (x <= y), j + (y <= x)
+        if i >= len(a) or j >= len(b):
+            break
+    return 1.0 - float(m) / float(w)

@@ -580,3 +580,50 @@ def test_literal_ambiguity_policy(orc):
         e.build()
         gi, gd = e.all_vs_all()
     assert np.array_equal(gi, oi) and np.array_equal(gd, od)
+
+
+@pytest.mark.parametrize("kind", [0, 1])
+def test_minhash_sketches_match_restatement(orc, kind):
+    """SequenceKmers.hashSet(width) and Sketch.distance (hash unpinned, switchable):
+    device sketches against the literal Python restatement -- DNA both strands (odd and even K, a set
+    smaller than the width = a "dwarf"), RNA, protein, both string hashes, several widths."""
+    rng = random.Random(31337 + kind)
+    base = _rand_dna(rng, 40000)
+    dna = [base, _mutate(rng, base, 0.02), _mutate(rng, base, 0.2), _rand_dna(rng, 30000), _rand_dna(rng, 150), "acgtn"]
+    for k, width in ((21, 360), (8, 100), (12, 2000), (4, 4096)):
+        psets = [orc.py_kmer_set(s, k) for s in dna]
+        want = [orc.py_hash_set(p, width, kind) for p in psets]
+        with gkd.Engine(k=k) as e:
+            for s in dna:
+                e.add(s)
+            e.build()
+            got = [e.hash_set(i, width, kind).tolist() for i in range(len(dna))]
+            assert got == want, (k, width)
+            a = [i for i in range(len(dna)) for j in range(len(dna))]
+            b = [j for i in range(len(dna)) for j in range(len(dna))]
+            d = e.sketch_distances(width, a, b, kind)
+            for t, (i, j) in enumerate(zip(a, b)):
+                assert d[t] == orc.py_sketch_distance(want[i], want[j]), (k, width, i, j)
+            # the estimate tracks the exact distance for a mutated descendant (sanity, not parity)
+            if k == 21:
+                exact = e.pair(0, 1)[2]
+                assert abs(d[1] - exact) < 0.15
+    aa = "ACDEFGHIKLMNPQRSTVWY"
+    prots = [_rand_dna(rng, 3000, aa), _rand_dna(rng, 50, aa)]
+    prots.append(_mutate(rng, prots[0], 0.05, aa))
+    for k in (8, 3):
+        want = [orc.py_hash_set(orc.py_kmer_set(p, k, orc.PROT), 360, kind) for p in prots]
+        with gkd.Engine(k=k, alphabet=gkd.PROT) as e:
+            for p in prots:
+                e.add(p)
+            e.build()
+            assert [e.hash_set(i, 360, kind).tolist() for i in range(3)] == want
+            assert e.sketch_distances(360, [0, 0], [2, 1], kind).tolist() == [orc.py_sketch_distance(want[0], want[2]),
+                                                                                orc.py_sketch_distance(want[0], want[1])]
+    with gkd.Engine(k=9, alphabet=gkd.RNA) as e:
+        s = _rand_dna(rng, 2000, "acgu")
+        e.add(s)
+        e.build()
+        assert e.hash_set(0, 50, kind).tolist() == orc.py_hash_set(orc.py_kmer_set(s, 9, orc.RNA), 50, kind)
+        with pytest.raises(gkd.GkdError):
+            e.hash_set(0, 5000, kind)

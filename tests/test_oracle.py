@@ -226,3 +226,23 @@ def test_numpy_generator_port_matches_the_engine_generator():
             a = np.empty(50021, dtype=np.uint8)
             gkd.synth(a, 0x5EED0000, fam, mem, rate, protein=protein)
             assert np.array_equal(a, osynth.synth(50021, 0x5EED0000, fam, mem, rate, protein=protein, chunk=7000))
+
+
+def test_sketch_restatement_known_answers(orc):
+    """String.hashCode and murmur3_x86_32 known answers, and the bottom-w estimator on hand-made signatures"""
+    assert orc.java_string_hash("") == 0 and orc.java_string_hash("a") == 97
+    assert orc.java_string_hash("hello") == 99162322
+    assert orc.java_string_hash("acgtacgtacgtacgtacgta") == orc._s32(sum(ord(c) * 31 ** (20 - i) for i, c in enumerate("acgtacgtacgtacgtacgta")))
+    # published murmur3_x86_32 vectors (seed 0)
+    assert orc.murmur3_32(b"") == 0
+    assert orc.murmur3_32(b"hello") & 0xFFFFFFFF == 0x248BFA47
+    assert orc.murmur3_32(b"The quick brown fox jumps over the lazy dog") & 0xFFFFFFFF == 0x2E4FF723
+    assert orc.py_sketch_distance([1, 2, 3], [1, 2, 3]) == 0.0
+    assert orc.py_sketch_distance([1, 2, 3], [4, 5, 6]) == 1.0
+    assert orc.py_sketch_distance([], [1]) == 1.0
+    assert orc.py_sketch_distance([-5, 1, 7, 9], [-5, 2, 7, 10]) == 0.5   # union order -5* 1 2 7* 9 10: the w=4 smallest hold 2 matches
+    assert orc.py_sketch_distance([-5, 1, 7, 9], [-5, 2, 8, 10]) == 0.75
+    assert orc.py_sketch_distance([1, 2], [1, 2, 3, 4]) == 0.0
+    ks = orc.py_kmer_set("acgtacgtta", 3)
+    hs = orc.py_hash_set(ks, 4)
+    assert hs == sorted(hs) and len(hs) == 4 and len(orc.py_hash_set(ks, 1000)) == len({orc.java_string_hash(k) for k in ks})
