@@ -53,7 +53,10 @@ def parse_args():
     ap.add_argument("--k", type=int, default=21)
     ap.add_argument("--panel", type=int, default=int(os.environ.get("GKD_BENCH_PANEL", "128")),
                     help="sets per exchanged panel (N>1)")
-    ap.add_argument("--cpu-sample", type=int, default=int(os.environ.get("GKD_BENCH_CPU_SAMPLE", "24")))
+    ap.add_argument("--cpu-sample", type=int, default=int(os.environ.get("GKD_BENCH_CPU_SAMPLE", "22")),
+                    help="largest CPU sample (genomes); the reference arm shrinks it to fit its time budget")
+    ap.add_argument("--cpu-budget", type=float, default=float(os.environ.get("GKD_BENCH_CPU_BUDGET_S", "240")),
+                    help="wall-clock budget (s) of the whole --impl reference run")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--other-configs", action="store_true", default=os.environ.get("GKD_BENCH_OTHER", "0") == "1",
@@ -80,8 +83,8 @@ def config_dict(a, world):
     n = a.genomes
     return {"workload": workload_name(a), "k": a.k, "genomes": n, "genome_bp": a.length, "pairs": n * (n - 1) // 2,
             "families": a.families,
-            "cpu_sample": f"CPU legs run the first {a.cpu_sample} genomes of this workload "
-                          f"({a.cpu_sample * (a.cpu_sample - 1) // 2} pairs) with the reference's batch=20 decomposition",
+            "cpu_sample": f"CPU legs run the first n <= {a.cpu_sample} genomes of this workload with the reference's "
+                          "batch=20 decomposition; n is chosen to fit the leg's time budget and stated in cpu_baseline.sample",
             "l2": "inputs (21 MB per set, 21 GB total) are far larger than L2; no flush needed"}
 
 
@@ -184,8 +187,26 @@ def cpu_phase_costs(a, seqs):
             "note": "HashSet<String> port; the reference pays one build per uncached column per pair plus one probe"}
 
 
-def cpu_baseline_block(a, value, dt, threads, pairs, extra=None):
-    sample = (f"first {a.cpu_sample} genomes of the workload ({pairs} pairs in {dt:.1f} s): reference decomposition, "
+def choose_sample(a, budget_s, phases, threads):
+    """largest sample (4 .. --cpu-sample genomes) whose modelled step time fits budget_s: the batch cache is
+    built serially, the pairs run on the rows' threads at ~50 % parallel efficiency (memory-bound probes)"""
+    tb, tp = phases["set_build_s_per_genome_1thread"], phases["probe_s_per_pair_1thread"]
+    best = 4
+    for n in range(4, max(4, a.cpu_sample) + 1):
+        cached = min(n, 20)
+        pairs_cached = cached * (cached - 1) // 2
+        pairs_rebuilt = n * (n - 1) // 2 - pairs_cached - max(0, n - 20) * (max(0, n - 20) - 1) // 2
+        later = max(0, n - 20)  # second batch: its own cache and pairs
+        t = cached * tb + later * tb + (pairs_cached * tp + later * (later - 1) // 2 * tp +
+                                         pairs_rebuilt * (tb + tp)) / max(1.0, 0.5 * min(threads, cached))
+        if t <= budget_s:
+            best = n
+    return best
+
+
+def cpu_baseline_block(a, value, dt, threads, pairs, extra=None, n_sample=None):
+    n_sample = n_sample or a.cpu_sample
+    sample = (f"first {n_sample} genomes of the workload ({pairs} pairs in {dt:.1f} s): reference decomposition, "
               f"batch=20 cached serially, rows in parallel on {threads} threads, uncached columns rebuilt per pair; "
               f"C port of the reference's HashSet<String> algorithm, not the JVM")
     blk = {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
@@ -199,24 +220,30 @@ def reference_main(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    seqs = host_sample(a, a.cpu_sample)
+    from oracle import oracle as orc
+
+    # size the per-step sample so that the whole run (warm-up + timed steps) fits the budget
+    seqs = host_sample(a, min(a.cpu_sample, 2))
+    phases = cpu_phase_costs(a, seqs)
+    n_sample = choose_sample(a, a.cpu_budget / max(1, a.warmup + a.steps), phases, orc.max_threads())
+    seqs = host_sample(a, n_sample)
     vals = []
     threads = pairs = 0
     for s in range(a.warmup + a.steps):
-        v, dt, threads, pairs = run_cpu_reference(a, a.cpu_sample, seqs)
+        v, dt, threads, pairs = run_cpu_reference(a, n_sample, seqs)
         if s >= a.warmup:
             vals.append((v, dt))
     value = sum(p for p, _ in vals) / len(vals)
     ms = 1e3 * sum(d for _, d in vals) / len(vals)
-    iv, idt, _, _ = run_cpu_reference(a, a.cpu_sample, seqs, mode=1)
+    iv, idt, _, _ = run_cpu_reference(a, n_sample, seqs, mode=1)
     extra = {"integer_mode": {"value": iv, "unit": UNIT, "seconds": idt,
                               "what": "same sample and decomposition on sorted canonical uint64 sets with a linear merge "
                                       "(not the reference's representation; shown so the string sets do not flatter the GPU)"},
-             "phases": cpu_phase_costs(a, seqs)}
+             "phases": phases}
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
             "warmup": a.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "u64", "data": "synthetic", "config": config_dict(a, a.gpus),
-            "cpu_baseline": cpu_baseline_block(a, value, ms / 1e3, threads, pairs, extra),
+            "cpu_baseline": cpu_baseline_block(a, value, ms / 1e3, threads, pairs, extra, n_sample),
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0, "product_library_loaded": "genome.distance_b200" in sys.modules}
     print(json.dumps(line), flush=True)

@@ -57,6 +57,20 @@ SYMBOLS = {
     "gkd_label": (C.c_char_p, [_vp, _u32]),
     "gkd_comment": (C.c_char_p, [_vp, _u32]),
     "gkd_count": (_u32, [_vp]),
+    "gkd_set_label": (_i32, [_vp, _u32, C.c_char_p, C.c_char_p]),
+    "gkd_group_create": (_i32, [C.POINTER(_vp), C.POINTER(GkdConfig), C.POINTER(C.c_int32), _u32]),
+    "gkd_group_destroy": (_i32, [_vp]),
+    "gkd_group_last_error": (C.c_char_p, [_vp]),
+    "gkd_group_size": (_u32, [_vp]),
+    "gkd_group_count": (_u32, [_vp]),
+    "gkd_group_member": (_vp, [_vp, _u32]),
+    "gkd_group_set_panel": (_i32, [_vp, _u32]),
+    "gkd_group_add_sequences": (_i32, [_vp, _u32, C.POINTER(_vp), _pu64, _u32, _pu32]),
+    "gkd_group_add_fasta_file": (_i32, [_vp, C.c_char_p, _pu32]),
+    "gkd_group_label": (C.c_char_p, [_vp, _u32]),
+    "gkd_group_comment": (C.c_char_p, [_vp, _u32]),
+    "gkd_group_build": (_i32, [_vp]),
+    "gkd_group_all_vs_all": (_i32, [_vp, _vp, _vp]),
     "gkd_build_sets": (_i32, [_vp]),
     "gkd_set_size": (_i32, [_vp, _u32, _pu64, _pu64, _pu64]),
     "gkd_export_set": (_i32, [_vp, _u32, _vp, _u64, _pu64]),

@@ -1116,6 +1116,16 @@ const char *gkd_label(const gkd_ctx *c, uint32_t id) { return (c && id < c->geno
 const char *gkd_comment(const gkd_ctx *c, uint32_t id) { return (c && id < c->genomes.size()) ? c->genomes[id].comment.c_str() : ""; }
 uint32_t gkd_count(const gkd_ctx *c) { return c ? (uint32_t)c->genomes.size() : 0; }
 
+int gkd_set_label(gkd_ctx *c, uint32_t id, const char *label, const char *comment) {
+    if (!c) return GKD_EINVAL;
+    if (id >= c->genomes.size()) return fail(c, GKD_EINVAL, "set id %u out of range (have %zu)", id, c->genomes.size());
+    ABI_GUARD_BEGIN
+    c->genomes[id].label = label ? label : "";
+    c->genomes[id].comment = comment ? comment : "";
+    return GKD_OK;
+    ABI_GUARD_END(c)
+}
+
 int gkd_build_sets(gkd_ctx *c) {
     CHECK_CTX(c);
     CK(cudaSetDevice(c->cfg.device));

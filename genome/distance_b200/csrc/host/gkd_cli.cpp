@@ -129,9 +129,56 @@ const std::vector<OptSpec> FASTA_OPTS = {
     {{"--type"}, true, "input sequence type"},
     {{"--output", "-o"}, true, "output file for report (if not STDOUT)"},
     {{"--device"}, true, "CUDA device ordinal (additive option; default 0)"},
+    {{"--gpus"}, true, "number of GPUs to shard the pair matrix over (additive option; default 1; needs --input)"},
+    {{"--devices"}, true, "explicit comma-separated device ordinals for the group, e.g. 0,1,2,3 (an ordinal may repeat)"},
+    {{"--metrics"}, true, "write one JSON line of engine metrics to this file (additive option)"},
     {{"--help", "-h"}, false, "display command-line usage"},
     {{"--verbose", "-v"}, false, "display more frequent log messages"},
 };
+
+// the report lines of fastaDist (:188-192), in list order
+template <class LabelFn, class CommentFn>
+size_t writePairs(std::ostream &writer, size_t n, const std::vector<double> &dist, LabelFn label, CommentFn comment) {
+    size_t t = 0;
+    std::string line;
+    for (size_t i = 0; i < n; i++) {
+        for (size_t j = i + 1; j < n; j++, t++) {
+            line.clear();
+            line += label(i);
+            line += '\t';
+            line += comment(i);
+            line += '\t';
+            line += label(j);
+            line += '\t';
+            line += comment(j);
+            line += '\t';
+            line += javaDouble(dist[t]);
+            line += '\n';
+            writer << line;
+        }
+    }
+    writer.flush();
+    return t;
+}
+
+void writeMetrics(const std::string &path, const std::string &command, gkd_ctx *ctx, size_t pairs, int gpus) {
+    if (path.empty()) return;
+    gkd_metrics m{};
+    if (ctx) gkd_get_metrics(ctx, &m);
+    std::ofstream f(path);
+    if (!f) throw IOException("Cannot open metrics file " + path + ".");
+    char buf[1024];
+    snprintf(buf, sizeof(buf),
+             "{\"command\": \"%s\", \"gpus\": %d, \"pairs\": %zu, \"pack_ms\": %.3f, \"encode_ms\": %.3f, \"sort_ms\": %.3f, "
+             "\"unique_ms\": %.3f, \"intersect_ms\": %.3f, \"epilogue_ms\": %.3f, \"residues_packed\": %llu, "
+             "\"kmer_positions\": %llu, \"keys_unique\": %llu, \"intersect_bytes\": %llu, \"h2d_bytes\": %llu, "
+             "\"d2h_bytes\": %llu, \"launches\": %llu, \"intersect_kernel\": %u, \"scope\": \"%s\"}\n",
+             command.c_str(), gpus, pairs, m.pack_ms, m.encode_ms, m.sort_ms, m.unique_ms, m.total_intersect_ms, m.epilogue_ms,
+             (unsigned long long)m.residues_packed, (unsigned long long)m.kmer_positions, (unsigned long long)m.keys_unique,
+             (unsigned long long)m.total_intersect_bytes, (unsigned long long)m.h2d_bytes, (unsigned long long)m.d2h_bytes,
+             (unsigned long long)m.launches, m.intersect_kernel, gpus > 1 ? "member 0 of the group" : "context");
+    f << buf;
+}
 
 int fastaDist(const std::vector<std::string> &args) {
     Parsed p = parseOptions(FASTA_OPTS, args);
@@ -160,6 +207,56 @@ int fastaDist(const std::vector<std::string> &args) {
     }
     std::ostream &writer = p.values.count("--output") ? (std::ostream &)ofile : std::cout;
 
+    int gpus = p.values.count("--gpus") ? toInt("--gpus", p.values["--gpus"]) : 1;
+    std::vector<int32_t> deviceList;
+    if (p.values.count("--devices")) {
+        std::string item;
+        for (char ch : p.values["--devices"] + ",") {
+            if (ch == ',') {
+                if (!item.empty()) deviceList.push_back(toInt("--devices", item));
+                item.clear();
+            } else item += ch;
+        }
+        if (deviceList.empty()) throw ParseFailureException("--devices needs at least one ordinal.");
+        gpus = (int)deviceList.size();
+    }
+    const std::string metricsFile = p.values.count("--metrics") ? p.values["--metrics"] : "";
+    if (gpus < 1) throw ParseFailureException("Number of GPUs must be at least 1.");
+    if (gpus > 1 || !deviceList.empty()) {
+        // the pair matrix sharded over a group of contexts, one per device (gkd_group_*); same report
+        if (inFile.empty()) throw ParseFailureException("--gpus needs an input file (--input).");
+        gkd_config cfg{};
+        cfg.k = kmerSize;
+        cfg.alphabet = (int)seqType;
+        std::vector<int32_t> devices = deviceList;
+        if (devices.empty())
+            for (int d = 0; d < gpus; d++) devices.push_back(device + d);
+        gkd_group *grp = nullptr;
+        if (gkd_group_create(&grp, &cfg, devices.data(), (uint32_t)devices.size()) != GKD_OK)
+            throw std::runtime_error(gkd_group_last_error(nullptr));
+        struct Closer {
+            gkd_group *g;
+            ~Closer() { gkd_group_destroy(g); }
+        } closer{grp};
+        auto gcheck = [&](int rc) {
+            if (rc == GKD_EIO) throw IOException(gkd_group_last_error(grp));
+            if (rc == GKD_EINVAL) throw ParseFailureException(gkd_group_last_error(grp));
+            if (rc != GKD_OK) throw std::runtime_error(gkd_group_last_error(grp));
+        };
+        uint32_t n = 0;
+        gcheck(gkd_group_add_fasta_file(grp, inFile.c_str(), &n));
+        logInfo(std::to_string(n) + " sequences read from input.");
+        writer << "seq1\tname1\tseq2\tname2\tdistance\n";
+        gcheck(gkd_group_build(grp));
+        logInfo(std::to_string(n) + " sequences cached on " + std::to_string(gpus) + " GPUs. Computing distances.");
+        std::vector<double> dist((size_t)n * (n > 0 ? n - 1 : 0) / 2);
+        gcheck(gkd_group_all_vs_all(grp, nullptr, dist.data()));
+        size_t t = writePairs(writer, n, dist, [&](size_t i) { return gkd_group_label(grp, (uint32_t)i); },
+                              [&](size_t i) { return gkd_group_comment(grp, (uint32_t)i); });
+        logInfo(std::to_string(t) + " pairs computed in 1 batches.");
+        writeMetrics(metricsFile, "fastaDist", gkd_group_member(grp, 0), t, gpus);
+        return 0;
+    }
     KmerEngine engine(seqType, kmerSize, device);
     std::vector<SequenceKmers> seqs = engine.addFasta(inFile.empty() ? "-" : inFile);
     logInfo(std::to_string(seqs.size()) + " sequences read from input.");
@@ -170,26 +267,10 @@ int fastaDist(const std::vector<std::string> &args) {
     logInfo(std::to_string(seqs.size()) + " sequences cached. Computing distances.");
     std::vector<double> dist;
     engine.allVsAll(nullptr, dist);
-    size_t t = 0;
-    std::string line;
-    for (size_t i = 0; i < seqs.size(); i++) {
-        for (size_t j = i + 1; j < seqs.size(); j++, t++) {
-            line.clear();
-            line += seqs[i].getGenomeId();
-            line += '\t';
-            line += seqs[i].getGenomeName();
-            line += '\t';
-            line += seqs[j].getGenomeId();
-            line += '\t';
-            line += seqs[j].getGenomeName();
-            line += '\t';
-            line += javaDouble(dist[t]);
-            line += '\n';
-            writer << line;
-        }
-    }
-    writer.flush();
+    size_t t = writePairs(writer, seqs.size(), dist, [&](size_t i) { return seqs[i].getGenomeId(); },
+                          [&](size_t i) { return seqs[i].getGenomeName(); });
     logInfo(std::to_string(t) + " pairs computed in 1 batches.");
+    writeMetrics(metricsFile, "fastaDist", engine.raw(), t, 1);
     return 0;
 }
 

@@ -339,3 +339,72 @@ def synth(dst, seed: int, family: int, member: int, rate: float, protein: bool =
     if rc:
         raise GkdError(rc, "synth failed")
     return dst
+
+
+class Group:
+    """Several devices in one process behind the C ABI (gkd_group_*): one context per listed device ordinal
+    (an ordinal may repeat), one host thread per member, peer copies of set arenas, no reduction."""
+
+    def __init__(self, devices: Sequence[int], k: int = 0, alphabet: int = DNA, strand_mode: int = STRAND_BOTH,
+                 workspace_bytes: int = 0, panel: int = 0):
+        self._L = _lib.load()
+        cfg = GkdConfig(device=0, k=k, alphabet=alphabet, strand_mode=strand_mode, workspace_bytes=workspace_bytes)
+        devs = (C.c_int32 * len(devices))(*devices)
+        h = C.c_void_p()
+        rc = self._L.gkd_group_create(C.byref(h), C.byref(cfg), devs, len(devices))
+        if rc:
+            raise GkdError(rc, (self._L.gkd_group_last_error(None) or b"").decode())
+        self._h = h
+        if panel:
+            self._ck(self._L.gkd_group_set_panel(self._h, panel))
+
+    def _ck(self, rc: int):
+        if rc:
+            raise GkdError(rc, (self._L.gkd_group_last_error(self._h) or b"").decode())
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.gkd_group_destroy(self._h)
+            self._h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def __len__(self) -> int:
+        return self._L.gkd_group_count(self._h)
+
+    def add(self, member: int, contigs) -> int:
+        """one genome on one member (members must be filled in ascending order); returns its global id"""
+        if isinstance(contigs, (str, bytes, bytearray, np.ndarray)):
+            contigs = [contigs]
+        triples = [Engine._ptr_len(c) for c in contigs]
+        n = len(triples)
+        ptrs = (C.c_void_p * max(n, 1))(*[t[0] for t in triples])
+        lens = (C.c_uint64 * max(n, 1))(*[t[1] for t in triples])
+        out = C.c_uint32()
+        self._ck(self._L.gkd_group_add_sequences(self._h, member, ptrs, lens, n, C.byref(out)))
+        return out.value
+
+    def add_fasta(self, path: str) -> int:
+        n = C.c_uint32()
+        self._ck(self._L.gkd_group_add_fasta_file(self._h, path.encode(), C.byref(n)))
+        return n.value
+
+    def label(self, i: int) -> str:
+        return self._L.gkd_group_label(self._h, i).decode("latin-1")
+
+    def comment(self, i: int) -> str:
+        return self._L.gkd_group_comment(self._h, i).decode("latin-1")
+
+    def build(self):
+        self._ck(self._L.gkd_group_build(self._h))
+
+    def all_vs_all(self):
+        n = len(self)
+        npairs = n * (n - 1) // 2
+        inter, dist = np.empty(npairs, dtype=np.uint64), np.empty(npairs, dtype=np.float64)
+        self._ck(self._L.gkd_group_all_vs_all(self._h, inter.ctypes.data, dist.ctypes.data))
+        return inter, dist

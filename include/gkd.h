@@ -131,6 +131,8 @@ int gkd_add_fasta_file(gkd_ctx *ctx, const char *path, int per_record, uint32_t 
 const char *gkd_label(const gkd_ctx *ctx, uint32_t id);
 const char *gkd_comment(const gkd_ctx *ctx, uint32_t id);
 uint32_t gkd_count(const gkd_ctx *ctx);
+/* attach a label and comment to a set that did not come from a FASTA file (copied) */
+int gkd_set_label(gkd_ctx *ctx, uint32_t id, const char *label, const char *comment);
 
 /* ---- set construction: kernels 2 + 3 ------------------------------------------------------- */
 /* Build the sorted unique canonical uint64 key set of every genome added since the last build. */
@@ -208,6 +210,33 @@ int gkd_pairs_ex(gkd_ctx *ctx, const uint32_t *a, const uint32_t *b, uint64_t n_
 /* SequenceKmers.distance(other) for one pair (DistanceRepsProcessor.java:101,190;
  * FastaDistanceRepsProcessor.java:128); uni = |A|+|B|-I */
 int gkd_pair(gkd_ctx *ctx, uint32_t a, uint32_t b, uint64_t *inter, uint64_t *uni, double *dist);
+
+/* ---- several GPUs in one process ------------------------------------------------------------------------
+ * A group is one context per listed device (an ordinal may be listed more than once) driven by one host thread
+ * per member.  The pair matrix of FastaDistanceProcessor.runReporter (:141-194) is cut into member blocks, the
+ * set arenas of the peers a member needs are pulled with peer copies (copy engines over NVLink; staged through
+ * the host where peer access is unavailable) while earlier blocks are being intersected, and adopted in place.
+ * There is no reduction.  Genomes get global ids in insertion order and must be added member by member
+ * (member 0 first), so every member owns a contiguous block of ids; results are indexed by global id exactly
+ * like gkd_all_vs_all, so a report produced through a group equals the single-GPU report byte for byte. */
+typedef struct gkd_group gkd_group;
+int gkd_group_create(gkd_group **out, const gkd_config *cfg /* device field ignored */, const int32_t *devices,
+                     uint32_t n_devices);
+int gkd_group_destroy(gkd_group *g);
+const char *gkd_group_last_error(const gkd_group *g);
+uint32_t gkd_group_size(const gkd_group *g);   /* members */
+uint32_t gkd_group_count(const gkd_group *g);  /* genomes */
+gkd_ctx *gkd_group_member(gkd_group *g, uint32_t member);
+int gkd_group_set_panel(gkd_group *g, uint32_t sets_per_panel);  /* sets moved per peer copy (default 128) */
+int gkd_group_add_sequences(gkd_group *g, uint32_t member, const char *const *contigs, const uint64_t *lens,
+                            uint32_t n_contigs, uint32_t *global_id);
+/* every record of a FASTA file, block-distributed over the members (FastaInputStream, per-record units) */
+int gkd_group_add_fasta_file(gkd_group *g, const char *path, uint32_t *n_added);
+const char *gkd_group_label(const gkd_group *g, uint32_t global_id);
+const char *gkd_group_comment(const gkd_group *g, uint32_t global_id);
+int gkd_group_build(gkd_group *g);  /* kernels 1-3 on every member concurrently */
+/* all pairs i < j over global ids, row-major strict upper triangle (either output may be NULL) */
+int gkd_group_all_vs_all(gkd_group *g, uint64_t *inter, double *dist);
 
 /* ---- MinHash sketches ---------------------------------------------------------
  * SequenceKmers.hashSet(width) and Sketch.distance (SketchProcessor.java:91, WidthProcessor.java:177-183,

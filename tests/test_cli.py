@@ -77,6 +77,16 @@ def test_fastadist_report_matches_oracle_text(orc, tmp_path):
     assert sorted(got[1:]) == sorted(want[1:])  # the reference's row order is nondeterministic
     assert got[-1].endswith("\t1.0")
     assert "7 sequences read from input." in err
+    # the same report through a group of contexts (--gpus path; three members on device 0 here): byte for byte
+    met = tmp_path / "m.json"
+    rc, out3, err = run(["fastaDist", "-i", str(fa), "--devices", "0,0,0", "--metrics", str(met)])
+    assert rc == 0, err
+    assert out3 == out and "sequences cached on 3 GPUs" in err
+    import json as _json
+    m = _json.loads(met.read_text())
+    assert m["command"] == "fastaDist" and m["gpus"] == 3 and m["pairs"] == 21 and m["launches"] > 0
+    rc, _, err = run(["fastaDist", "--gpus", "2"], stdin=">a\nacgt\n")
+    assert rc != 0 and "--gpus needs an input file" in err
     # stdin + -o + protein type + explicit K
     prot = ">p1 a\nMKVLAAGIVGLLLAQWERTY\n>p2 b\nMKVLAAGIVGLLLSQWERTY\n"
     outp = tmp_path / "o.tbl"

@@ -627,3 +627,61 @@ def test_minhash_sketches_match_restatement(orc, kind):
         assert e.hash_set(0, 50, kind).tolist() == orc.py_hash_set(orc.py_kmer_set(s, 9, orc.RNA), 50, kind)
         with pytest.raises(gkd.GkdError):
             e.hash_set(0, 5000, kind)
+
+
+def test_group_of_contexts_matches_single_context(orc):
+    """gkd_group_*: several contexts in one process (here all on device 0; on a multi-GPU box one per device),
+    one host thread per member, set arenas pulled with peer copies and adopted in place.  Results are indexed
+    by global id exactly like the single-context call -- odd and even member counts (the half-way block of an
+    even ring is split), ragged slices, several arenas per member, even K (palindrome sub-sets travel too)."""
+    import torch
+
+    rng = random.Random(808)
+    base = _rand_dna(rng, 50000)
+    seqs = [_mutate(rng, base, 0.01 * (i % 5)) if i % 4 else _rand_dna(rng, 20000 + 3000 * i) for i in range(13)]
+    seqs[5] = ""
+    for k in (21, 20):
+        with gkd.Engine(k=k) as e:
+            for s in seqs:
+                e.add(s)
+            e.build()
+            want_i, want_d = e.all_vs_all()
+        ndev = torch.cuda.device_count()
+        for members in (2, 3, 4):
+            devices = [m % ndev for m in range(members)]
+            with gkd.Group(devices, k=k, workspace_bytes=4 << 20, panel=2) as g:
+                per = (len(seqs) + members - 1) // members
+                for i, s in enumerate(seqs):
+                    assert g.add(min(i // per, members - 1), s) == i
+                g.build()
+                gi, gd = g.all_vs_all()
+            assert np.array_equal(gi, want_i) and np.array_equal(gd, want_d), (k, members)
+    with gkd.Group([0, 0], k=21) as g:
+        g.add(1, "acgtacgtacgtacgtacgtacgtacgt")
+        with pytest.raises(gkd.GkdError):  # members own contiguous id blocks: member 0 can no longer be filled
+            g.add(0, "acgt")
+
+
+def test_contexts_on_every_visible_device_in_one_process(orc):
+    """function attributes (opt-in shared memory) are per device: every context sets them for its own device,
+    so a process may hold contexts on all GPUs at once (one per device here, used alternately)"""
+    import torch
+
+    seqs = _np_family(9, 4, 300000, [0.02])
+    want = None
+    engines = [gkd.Engine(k=21, device=d) for d in range(torch.cuda.device_count())]
+    try:
+        for e in engines:
+            for s in seqs:
+                e.add(s)
+        for e in engines:
+            e.build()
+        for e in engines:
+            gi, gd = e.all_vs_all()
+            if want is None:
+                osets = [orc.IntSet(s, 21) for s in seqs]
+                want = [osets[i].similarity(osets[j]) for i in range(4) for j in range(i + 1, 4)]
+            assert gi.tolist() == want
+    finally:
+        for e in engines:
+            e.close()
