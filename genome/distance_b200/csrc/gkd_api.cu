@@ -112,6 +112,8 @@ struct gkd_ctx {
     DevBuf keys_a, keys_b, tile_hist, tile_uniq, genome_counts, batch_genomes, set_build;
     DevBuf d_sets, counts, pal_counts, d_inter, d_dist, d_ca, d_cb, ids_a, ids_b, work_counter;
     DevBuf sk_cand, sk_misc, sk_sig, sk_len, sk_out;
+    DevBuf msd_genomes, msd_bins32, msd_bins64, msd_gstat;
+    bool use_msd = true;  // GKD_SORT_ALGO=lsd pins the LSD path
     bool sets_dirty = true;
 
     std::unordered_map<std::string, uint32_t> lit_dict;  // GKD_AMBIG_LITERAL: literal k-mer -> dense id
@@ -521,6 +523,132 @@ int finish_batch(gkd_ctx *c, const std::vector<BatchGenome> &bg, const std::vect
     return GKD_OK;
 }
 
+void record_set(gkd_ctx *c, uint32_t id, const gkd_packed_set &p, int arena_idx, const char *base) {
+    GenomeRec &g = c->genomes[id];
+    g.packed = p;
+    g.arena = arena_idx;
+    set_desc_from_packed(g, base);
+    g.built = true;
+    c->m.keys_unique += p.n;
+}
+
+// Kernel 3, fast path (sort_msd.cu): the batch's raw slots (h per slot in keys_a) -> finished bucketed sets.
+// Returns GKD_OK and *done = true when the sets were built; *done = false when the batch has to take the LSD
+// path (a bin outgrew the shared-memory capacity: heavily repeated k-mers).
+int finish_batch_msd(gkd_ctx *c, const std::vector<BatchGenome> &bg, const std::vector<uint32_t> &ids, const SortPlan &plan,
+                     uint32_t n_tiles, bool *done) {
+    *done = false;
+    const uint32_t n = (uint32_t)bg.size();
+    std::vector<MsdGenome> msd(n);
+    uint32_t n_bins = 0, max_p = 0;
+    for (uint32_t i = 0; i < n; i++) {
+        uint32_t p = level_for(bg[i].n_slots, MSD_BIN_AVG);
+        p = std::min<uint32_t>(std::min<uint32_t>(p, MSD_MAX_P), (uint32_t)c->key_bits);
+        msd[i] = MsdGenome{n_bins, p, 0, 0, nullptr, nullptr};
+        n_bins += 1u << p;
+        max_p = std::max(max_p, p);
+    }
+    int rc;
+    if ((rc = ensure(c, c->msd_genomes, n * sizeof(MsdGenome)))) return rc;
+    if ((rc = ensure(c, c->msd_bins32, (uint64_t)n_bins * 8))) return rc;    // bin_count | bin_cursor
+    if ((rc = ensure(c, c->msd_bins64, (uint64_t)n_bins * 16))) return rc;   // bin_start | status
+    if ((rc = ensure(c, c->msd_gstat, (uint64_t)n * 12))) return rc;         // valid | maxbin | unique
+    MsdPlan mp{};
+    mp.n_bins = n_bins;
+    mp.max_p = max_p;
+    mp.key_bits = c->key_bits;
+    mp.keys_in = plan.keys_a;
+    mp.keys_out = plan.keys_b;
+    mp.bin_count = (uint32_t *)c->msd_bins32.p;
+    mp.bin_cursor = mp.bin_count + n_bins;
+    mp.bin_start = (uint64_t *)c->msd_bins64.p;
+    mp.status = (unsigned long long *)(mp.bin_start + n_bins);
+    mp.genome_valid = (uint32_t *)c->msd_gstat.p;
+    mp.genome_maxbin = mp.genome_valid + n;
+    mp.genome_unique = mp.genome_maxbin + n;
+    CK(cudaMemcpyAsync(c->msd_genomes.p, msd.data(), n * sizeof(MsdGenome), cudaMemcpyHostToDevice, c->stream));
+    CK(launch_msd_partition((const BatchGenome *)c->batch_genomes.p, n, n_tiles, (const MsdGenome *)c->msd_genomes.p, mp, c->stream));
+    c->m.launches += 3;
+    std::vector<uint32_t> stat(2 * (size_t)n);
+    CK(cudaMemcpyAsync(stat.data(), mp.genome_valid, 2 * (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaEventRecord(c->ev[2], c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    for (uint32_t i = 0; i < n; i++)
+        if (stat[n + i] > MSD_BIN_CAP) return GKD_OK;  // *done stays false: LSD path
+    // arena: the distinct count is only known after the bin sort, so the low words get room for every valid slot
+    // (duplicates are a fraction of a percent of a genome's k-mers) and the table level comes from that bound
+    const uint64_t lsz = c->low_bits / 8;
+    std::vector<gkd_packed_set> packed(n);
+    uint64_t cur = 0;
+    uint32_t max_s = 0;
+    for (uint32_t i = 0; i < n; i++) {
+        gkd_packed_set &p = packed[i];
+        p = gkd_packed_set{};
+        const uint32_t n_valid = stat[i];
+        p.level = std::max(set_level(n_valid, c->table_tmax, c->key_bits, c->low_bits), msd[i].p);
+        msd[i].level = p.level;
+        msd[i].s = std::max(p.level - msd[i].p, std::min<uint32_t>(MSD_SORT_BITS, (uint32_t)c->key_bits - msd[i].p));
+        if (msd[i].s > MSD_MAX_S) return GKD_OK;  // table finer than a bin sort can serve (tiny key spaces): LSD path
+        max_s = std::max(max_s, msd[i].s);
+        cur = (cur + SET_BLOCK_ALIGN - 1) & ~(SET_BLOCK_ALIGN - 1);
+        p.offs_off = cur;
+        cur += align16(((1ull << p.level) + 1) * 4);
+        p.lows_off = cur;
+        cur += align16((uint64_t)n_valid * lsz) + 16;
+    }
+    mp.max_s = max_s;
+    const uint64_t need = cur + 256;
+    void *arena = nullptr;
+    uint64_t cap = 0;
+    if ((rc = arena_alloc(c, need, &arena, &cap))) return rc;
+    c->arenas.push_back(Arena{(char *)arena, need, cap, ids.empty() ? 0u : ids.front(), n, true});
+    const int arena_idx = (int)c->arenas.size() - 1;
+    char *base = (char *)arena;
+    for (uint32_t i = 0; i < n; i++) {
+        msd[i].offs = (uint32_t *)(base + packed[i].offs_off);
+        msd[i].lows = base + packed[i].lows_off;
+    }
+    CK(cudaMemcpyAsync(c->msd_genomes.p, msd.data(), n * sizeof(MsdGenome), cudaMemcpyHostToDevice, c->stream));
+    CK(launch_msd_binsort((const MsdGenome *)c->msd_genomes.p, n, mp, c->low_bits, c->stream));
+    c->m.launches++;
+    std::vector<uint32_t> uniq(n);
+    CK(cudaMemcpyAsync(uniq.data(), mp.genome_unique, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    for (uint32_t i = 0; i < n; i++) {
+        packed[i].n = uniq[i];
+        record_set(c, ids[i], packed[i], arena_idx, base);
+    }
+    c->sets_dirty = true;
+    *done = true;
+    return GKD_OK;
+}
+
+// raw slots in plan.keys_a -> finished sets: the MSD bucket sort where it applies, else LSD radix sort + unique
+int sort_and_finish(gkd_ctx *c, const std::vector<BatchGenome> &bg, const std::vector<uint32_t> &ids, const SortPlan &plan,
+                    uint32_t n_tiles) {
+    bool done = false;
+    c->m.sort_passes = 0;
+    if (c->use_msd && !has_pal_lists(c)) {
+        NvtxRange nvtx("gkd kernel 3: MSD partition + bin sort");
+        int rc = finish_batch_msd(c, bg, ids, plan, n_tiles, &done);
+        if (rc) return rc;
+        if (done) {
+            c->m.sort_passes = 2;
+            return GKD_OK;
+        }
+    }
+    uint64_t *sorted = nullptr;
+    uint32_t passes = 0;
+    nvtxRangePushA("gkd kernel 3: LSD radix sort");
+    CK(launch_sort((const BatchGenome *)c->batch_genomes.p, plan, &sorted, &passes, c->stream));
+    nvtxRangePop();
+    c->m.launches += 3ull * passes;
+    c->m.sort_passes = passes;
+    CK(cudaEventRecord(c->ev[2], c->stream));
+    NvtxRange nvtx("gkd kernel 3: unique + bucket tables");
+    return finish_batch(c, bg, ids, plan, sorted);
+}
+
 int plan_batch(gkd_ctx *c, std::vector<BatchGenome> &bg, SortPlan &plan, uint64_t raw_keys, uint32_t n_tiles) {
     int rc;
     if ((rc = ensure(c, c->keys_a, raw_keys * 8))) return rc;
@@ -572,19 +700,8 @@ int build_batch(gkd_ctx *c, uint32_t first, uint32_t last) {
     nvtxRangePop();
     if (tiles) c->m.launches++;
     CK(cudaEventRecord(c->ev[1], c->stream));
-    uint64_t *sorted = nullptr;
-    uint32_t passes = 0;
-    nvtxRangePushA("gkd kernel 3: radix sort");
-    CK(launch_sort((const BatchGenome *)c->batch_genomes.p, plan, &sorted, &passes, c->stream));
-    nvtxRangePop();
-    c->m.launches += 3ull * passes;
-    c->m.sort_passes = passes;
     c->m.keys_sorted += raw;
-    CK(cudaEventRecord(c->ev[2], c->stream));
-    {
-        NvtxRange nvtx("gkd kernel 3: unique + bucket tables");
-        rc = finish_batch(c, bg, ids, plan, sorted);
-    }
+    rc = sort_and_finish(c, bg, ids, plan, tiles);  // records ev[2] between the sort and the unique / bin-sort stage
     if (rc) return rc;
     CK(cudaEventRecord(c->ev[3], c->stream));
     CK(cudaStreamSynchronize(c->stream));
@@ -635,12 +752,8 @@ int import_device_batch(gkd_ctx *c, const uint64_t *keys, const uint64_t *offset
         CK(launch_mix_keys(plan.keys_a, total, c->mix, c->stream));
         c->m.launches++;
     }
-    uint64_t *sorted = nullptr;
-    uint32_t passes = 0;
-    CK(launch_sort((const BatchGenome *)c->batch_genomes.p, plan, &sorted, &passes, c->stream));
-    c->m.launches += 3ull * passes;
     for (uint32_t i = i0; i < i1; i++) c->genomes.push_back(GenomeRec());
-    rc = finish_batch(c, bg, ids, plan, sorted);
+    rc = sort_and_finish(c, bg, ids, plan, tiles);
     if (rc) c->genomes.resize(id0);
     return rc;
 }
@@ -966,6 +1079,8 @@ int gkd_create(gkd_ctx **out, const gkd_config *cfg) {
     CK_CREATE(intersect_configure());
     CK_CREATE(sort_configure());
     CK_CREATE(sketch_configure());
+    CK_CREATE(msd_configure());
+    if (const char *a = getenv("GKD_SORT_ALGO")) c->use_msd = !(a[0] == 'l' || a[0] == 'L');
 #undef CK_CREATE
     *out = c;
     return GKD_OK;
@@ -1036,7 +1151,7 @@ int gkd_destroy(gkd_ctx *c) {
     DevBuf *bufs[] = {&c->keys_a, &c->keys_b, &c->tile_hist, &c->tile_uniq, &c->genome_counts, &c->batch_genomes,
                       &c->set_build, &c->d_sets, &c->counts, &c->pal_counts, &c->d_inter, &c->d_dist, &c->d_ca,
                       &c->d_cb, &c->ids_a, &c->ids_b, &c->work_counter, &c->sk_cand, &c->sk_misc, &c->sk_sig,
-                      &c->sk_len, &c->sk_out};
+                      &c->sk_len, &c->sk_out, &c->msd_genomes, &c->msd_bins32, &c->msd_bins64, &c->msd_gstat};
     for (DevBuf *b : bufs)
         if (b->p) cudaFreeAsync(b->p, c->stream);
     cudaStreamSynchronize(c->stream);

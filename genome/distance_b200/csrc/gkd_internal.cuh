@@ -195,6 +195,32 @@ struct SetBuild {
 };
 cudaError_t launch_unique_write(const BatchGenome *genomes, const SortPlan &plan, const uint64_t *sorted,
                                 const SetBuild *dst, int alphabet, int k, MixParams mix, int low_bits, cudaStream_t s);
+// kernel 3, fast path (sort_msd.cu): MSD partition by the top bits of h + one in-shared-memory sort per bin
+constexpr uint32_t MSD_BIN_AVG = 4096;  // a genome gets 2^p bins, p smallest with n_slots <= MSD_BIN_AVG << p
+constexpr uint32_t MSD_BIN_CAP = 5120;  // keys a bin-sort CTA holds; a fuller bin sends the batch to the LSD path
+constexpr uint32_t MSD_MAX_P = 12, MSD_SORT_BITS = 9, MSD_MAX_S = 12;
+struct MsdGenome {
+    uint32_t bin_first;  // index of the genome's first bin in the batch bin arrays
+    uint32_t p;          // bin bits
+    uint32_t s;          // sort-bucket bits inside a bin (p + s >= level)
+    uint32_t level;      // table level of the finished set (>= p)
+    void *lows;          // arena destinations
+    uint32_t *offs;
+};
+struct MsdPlan {
+    uint32_t n_bins, max_p, max_s;
+    int key_bits;
+    const uint64_t *keys_in;  // h per slot (KEY_SENTINEL = invalid)
+    uint64_t *keys_out;       // the same keys grouped by bin
+    uint32_t *bin_count, *bin_cursor;
+    uint64_t *bin_start;
+    unsigned long long *status;
+    uint32_t *genome_valid, *genome_maxbin, *genome_unique;
+};
+cudaError_t msd_configure();
+cudaError_t launch_msd_partition(const BatchGenome *genomes, uint32_t n_genomes, uint32_t n_tiles, const MsdGenome *msd,
+                                 const MsdPlan &plan, cudaStream_t s);
+cudaError_t launch_msd_binsort(const MsdGenome *msd, uint32_t n_genomes, const MsdPlan &plan, int low_bits, cudaStream_t s);
 // in-place key -> h for imported key arrays (keys outside the key space become KEY_SENTINEL)
 cudaError_t launch_mix_keys(uint64_t *keys, uint64_t n, MixParams mix, cudaStream_t s);
 // bucketed set -> original keys (unsorted: ascending h order), for export

@@ -685,3 +685,46 @@ def test_contexts_on_every_visible_device_in_one_process(orc):
     finally:
         for e in engines:
             e.close()
+
+
+@pytest.mark.parametrize("algo", ["msd", "lsd"])
+def test_both_kernel3_paths_build_identical_sets(orc, algo, monkeypatch):
+    """kernel 3 has a fast path (MSD partition by the top bits of the mixed key + one shared-memory sort per bin,
+    decoupled look-back for the output position) and the LSD radix path it falls back to.  GKD_SORT_ALGO pins
+    one; both must produce the oracle's sets -- random genomes of several sizes (one bin ... thousands of
+    bins), mostly-invalid text, a heavily repeated k-mer that overflows a bin (forces the fallback inside the
+    MSD path), empty input, protein, and a batch that mixes all of them."""
+    monkeypatch.setenv("GKD_SORT_ALGO", algo)
+    rng = random.Random(77)
+    big = np.empty(3_000_000, dtype=np.uint8)
+    gkd.synth(big, 5, 1, 0, 0.0)
+    genomes = [
+        [big.tobytes()],
+        [_rand_dna(rng, 70_000)],
+        [_rand_dna(rng, 9000), _rand_dna(rng, 5000, "acgtn"), ""],
+        ["n" * 50_000 + _rand_dna(rng, 300) + "n" * 50_000],          # 100,000 slots, a few hundred valid
+        [""],
+        [_rand_dna(rng, 4095 + 20), _rand_dna(rng, 4096 + 21)],        # bin-count boundaries
+    ]
+    repeats = [["a" * 40_000 + _rand_dna(rng, 20_000) + "acgt" * 5000]]  # > 5120 copies of one k-mer in one bin
+    for k, batch in ((21, genomes), (21, genomes + repeats), (13, genomes[1:] + repeats), (5, genomes[1:3])):
+        with gkd.Engine(k=k) as e:
+            for g in batch:
+                e.add(g)
+            e.build()
+            for i, g in enumerate(batch):
+                o = orc.IntSet(g, k)
+                assert e.set_size(i) == (len(o), o.count, o.palindromes), (algo, k, i)
+                assert np.array_equal(e.export_set(i), o.keys()), (algo, k, i)
+            gi, gd = e.all_vs_all()
+            assert gd[0] == orc.IntSet(batch[0], k).distance(orc.IntSet(batch[1], k))
+    aa = "ACDEFGHIKLMNPQRSTVWY"
+    prots = [[_rand_dna(rng, 60_000, aa)], [_rand_dna(rng, 300, aa) for _ in range(40)], ["MKV"]]
+    for k in (8, 5, 2):
+        with gkd.Engine(k=k, alphabet=gkd.PROT) as e:
+            for p in prots:
+                e.add(p)
+            e.build()
+            for i, p in enumerate(prots):
+                o = orc.IntSet(p, k, orc.PROT)
+                assert e.set_size(i)[1] == o.count and np.array_equal(e.export_set(i), o.keys()), (algo, k, i)
