@@ -532,71 +532,90 @@ void record_set(gkd_ctx *c, uint32_t id, const gkd_packed_set &p, int arena_idx,
     c->m.keys_unique += p.n;
 }
 
-// Kernel 3, fast path (sort_msd.cu): the batch's raw slots (h per slot in keys_a) -> finished bucketed sets.
-// Returns GKD_OK and *done = true when the sets were built; *done = false when the batch has to take the LSD
-// path (a bin outgrew the shared-memory capacity: heavily repeated k-mers).
-int finish_batch_msd(gkd_ctx *c, const std::vector<BatchGenome> &bg, const std::vector<uint32_t> &ids, const SortPlan &plan,
-                     uint32_t n_tiles, bool *done) {
+// Kernel 3, fast path (sort_msd.cu).  keys_in == nullptr: kernel 2 encodes the batch straight into fixed-capacity
+// bins (fused pass); else the given h values (imports) are partitioned.  Returns GKD_OK and *done = true when the
+// sets were built; *done = false when the batch has to take the LSD path (a bin overflowed: heavily repeated
+// k-mers, or a key space too small to bucket).
+int build_batch_msd(gkd_ctx *c, const std::vector<BatchGenome> &bg, const std::vector<uint32_t> &ids, uint32_t n_tiles,
+                    const uint64_t *keys_in, bool *done) {
     *done = false;
     const uint32_t n = (uint32_t)bg.size();
     std::vector<MsdGenome> msd(n);
     uint32_t n_bins = 0, max_p = 0;
+    uint64_t bin_keys = 0;
+    bool narrow = true;  // key_bits - p <= 32 everywhere: the bin sort keeps 32-bit keys in shared memory
     for (uint32_t i = 0; i < n; i++) {
         uint32_t p = level_for(bg[i].n_slots, MSD_BIN_AVG);
+        // big genomes get at least key_bits - 32 bin bits, so the bin sort can keep 32-bit keys in shared memory
+        if (bg[i].n_slots >= (1u << 18) && c->key_bits > 32) p = std::max<uint32_t>(p, (uint32_t)c->key_bits - 32);
         p = std::min<uint32_t>(std::min<uint32_t>(p, MSD_MAX_P), (uint32_t)c->key_bits);
-        msd[i] = MsdGenome{n_bins, p, 0, 0, nullptr, nullptr};
+        const double mean = (double)bg[i].n_slots / (double)(1u << p);
+        uint32_t cap = (uint32_t)(mean + 8.0 * std::sqrt(mean) + 64.0);
+        cap = std::min<uint32_t>((cap + 3) & ~3u, MSD_BIN_CAP);
+        if (mean > MSD_BIN_AVG) return GKD_OK;  // more than 2^MSD_MAX_P full bins: LSD path
+        MsdGenome &M = msd[i];
+        M = MsdGenome{};
+        M.bin_first = n_bins;
+        M.p = p;
+        M.s = std::min<uint32_t>(MSD_SORT_BITS, (uint32_t)c->key_bits - p);
+        M.cap = cap;
+        M.bins_off = bin_keys;
         n_bins += 1u << p;
+        bin_keys += (uint64_t)cap << p;
         max_p = std::max(max_p, p);
+        narrow = narrow && (c->key_bits - (int)p <= 32);
     }
     int rc;
+    if ((rc = ensure(c, c->keys_b, std::max<uint64_t>(bin_keys, 16) * 8))) return rc;
     if ((rc = ensure(c, c->msd_genomes, n * sizeof(MsdGenome)))) return rc;
-    if ((rc = ensure(c, c->msd_bins32, (uint64_t)n_bins * 8))) return rc;    // bin_count | bin_cursor
-    if ((rc = ensure(c, c->msd_bins64, (uint64_t)n_bins * 16))) return rc;   // bin_start | status
-    if ((rc = ensure(c, c->msd_gstat, (uint64_t)n * 12))) return rc;         // valid | maxbin | unique
+    if ((rc = ensure(c, c->msd_bins32, (uint64_t)n_bins * 4 + 16))) return rc;  // bin_cursor | overflow flag
+    if ((rc = ensure(c, c->msd_bins64, (uint64_t)n_bins * 8))) return rc;       // look-back status
+    if ((rc = ensure(c, c->msd_gstat, (uint64_t)n * 12))) return rc;            // valid | maxbin | unique
     MsdPlan mp{};
     mp.n_bins = n_bins;
     mp.max_p = max_p;
     mp.key_bits = c->key_bits;
-    mp.keys_in = plan.keys_a;
-    mp.keys_out = plan.keys_b;
-    mp.bin_count = (uint32_t *)c->msd_bins32.p;
-    mp.bin_cursor = mp.bin_count + n_bins;
-    mp.bin_start = (uint64_t *)c->msd_bins64.p;
-    mp.status = (unsigned long long *)(mp.bin_start + n_bins);
+    mp.bins = (uint64_t *)c->keys_b.p;
+    mp.bin_cursor = (uint32_t *)c->msd_bins32.p;
+    mp.overflow = mp.bin_cursor + n_bins;
+    mp.status = (unsigned long long *)c->msd_bins64.p;
     mp.genome_valid = (uint32_t *)c->msd_gstat.p;
     mp.genome_maxbin = mp.genome_valid + n;
     mp.genome_unique = mp.genome_maxbin + n;
     CK(cudaMemcpyAsync(c->msd_genomes.p, msd.data(), n * sizeof(MsdGenome), cudaMemcpyHostToDevice, c->stream));
-    CK(launch_msd_partition((const BatchGenome *)c->batch_genomes.p, n, n_tiles, (const MsdGenome *)c->msd_genomes.p, mp, c->stream));
-    c->m.launches += 3;
+    CK(cudaMemsetAsync(mp.bin_cursor, 0, (size_t)n_bins * 4 + 16, c->stream));
+    CK(cudaMemsetAsync(mp.status, 0, (size_t)n_bins * 8, c->stream));
+    nvtxRangePushA(keys_in ? "gkd kernel 3: partition into bins" : "gkd kernels 2+3: encode + mix + partition into bins");
+    CK(launch_encode_scatter((const BatchGenome *)c->batch_genomes.p, n, n_tiles, (const MsdGenome *)c->msd_genomes.p, max_p,
+                             c->cfg.alphabet, c->k, c->mix, keys_in, mp.bins, mp.bin_cursor, mp.overflow, c->stream));
+    nvtxRangePop();
+    CK(launch_msd_totals((const MsdGenome *)c->msd_genomes.p, n, mp, c->stream));
+    c->m.launches += 2;
     std::vector<uint32_t> stat(2 * (size_t)n);
+    uint32_t overflow = 0;
     CK(cudaMemcpyAsync(stat.data(), mp.genome_valid, 2 * (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(&overflow, mp.overflow, 4, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaEventRecord(c->ev[1], c->stream));
     CK(cudaEventRecord(c->ev[2], c->stream));
     CK(cudaStreamSynchronize(c->stream));
-    for (uint32_t i = 0; i < n; i++)
-        if (stat[n + i] > MSD_BIN_CAP) return GKD_OK;  // *done stays false: LSD path
+    if (overflow) return GKD_OK;  // *done stays false: LSD path
     // arena: the distinct count is only known after the bin sort, so the low words get room for every valid slot
     // (duplicates are a fraction of a percent of a genome's k-mers) and the table level comes from that bound
     const uint64_t lsz = c->low_bits / 8;
     std::vector<gkd_packed_set> packed(n);
     uint64_t cur = 0;
-    uint32_t max_s = 0;
     for (uint32_t i = 0; i < n; i++) {
         gkd_packed_set &p = packed[i];
         p = gkd_packed_set{};
         const uint32_t n_valid = stat[i];
         p.level = std::max(set_level(n_valid, c->table_tmax, c->key_bits, c->low_bits), msd[i].p);
         msd[i].level = p.level;
-        msd[i].s = std::max(p.level - msd[i].p, std::min<uint32_t>(MSD_SORT_BITS, (uint32_t)c->key_bits - msd[i].p));
-        if (msd[i].s > MSD_MAX_S) return GKD_OK;  // table finer than a bin sort can serve (tiny key spaces): LSD path
-        max_s = std::max(max_s, msd[i].s);
         cur = (cur + SET_BLOCK_ALIGN - 1) & ~(SET_BLOCK_ALIGN - 1);
         p.offs_off = cur;
         cur += align16(((1ull << p.level) + 1) * 4);
         p.lows_off = cur;
         cur += align16((uint64_t)n_valid * lsz) + 16;
     }
-    mp.max_s = max_s;
     const uint64_t need = cur + 256;
     void *arena = nullptr;
     uint64_t cap = 0;
@@ -609,7 +628,9 @@ int finish_batch_msd(gkd_ctx *c, const std::vector<BatchGenome> &bg, const std::
         msd[i].lows = base + packed[i].lows_off;
     }
     CK(cudaMemcpyAsync(c->msd_genomes.p, msd.data(), n * sizeof(MsdGenome), cudaMemcpyHostToDevice, c->stream));
-    CK(launch_msd_binsort((const MsdGenome *)c->msd_genomes.p, n, mp, c->low_bits, c->stream));
+    nvtxRangePushA("gkd kernel 3: bin sort + unique + bucket tables");
+    CK(launch_msd_binsort((const MsdGenome *)c->msd_genomes.p, n, mp, c->low_bits, narrow, c->stream));
+    nvtxRangePop();
     c->m.launches++;
     std::vector<uint32_t> uniq(n);
     CK(cudaMemcpyAsync(uniq.data(), mp.genome_unique, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
@@ -619,24 +640,13 @@ int finish_batch_msd(gkd_ctx *c, const std::vector<BatchGenome> &bg, const std::
         record_set(c, ids[i], packed[i], arena_idx, base);
     }
     c->sets_dirty = true;
+    c->m.sort_passes = 1;
     *done = true;
     return GKD_OK;
 }
 
-// raw slots in plan.keys_a -> finished sets: the MSD bucket sort where it applies, else LSD radix sort + unique
-int sort_and_finish(gkd_ctx *c, const std::vector<BatchGenome> &bg, const std::vector<uint32_t> &ids, const SortPlan &plan,
-                    uint32_t n_tiles) {
-    bool done = false;
-    c->m.sort_passes = 0;
-    if (c->use_msd && !has_pal_lists(c)) {
-        NvtxRange nvtx("gkd kernel 3: MSD partition + bin sort");
-        int rc = finish_batch_msd(c, bg, ids, plan, n_tiles, &done);
-        if (rc) return rc;
-        if (done) {
-            c->m.sort_passes = 2;
-            return GKD_OK;
-        }
-    }
+// raw slots in plan.keys_a -> finished sets on the LSD path: radix sort + unique
+int sort_and_finish_lsd(gkd_ctx *c, const std::vector<BatchGenome> &bg, const std::vector<uint32_t> &ids, const SortPlan &plan) {
     uint64_t *sorted = nullptr;
     uint32_t passes = 0;
     nvtxRangePushA("gkd kernel 3: LSD radix sort");
@@ -648,6 +658,8 @@ int sort_and_finish(gkd_ctx *c, const std::vector<BatchGenome> &bg, const std::v
     NvtxRange nvtx("gkd kernel 3: unique + bucket tables");
     return finish_batch(c, bg, ids, plan, sorted);
 }
+
+bool msd_applies(const gkd_ctx *c) { return c->use_msd && !has_pal_lists(c); }
 
 int plan_batch(gkd_ctx *c, std::vector<BatchGenome> &bg, SortPlan &plan, uint64_t raw_keys, uint32_t n_tiles) {
     int rc;
@@ -694,15 +706,25 @@ int build_batch(gkd_ctx *c, uint32_t first, uint32_t last) {
     int rc = plan_batch(c, bg, plan, std::max<uint64_t>(raw, 16), tiles);
     if (rc) return rc;
     CK(cudaEventRecord(c->ev[0], c->stream));
-    nvtxRangePushA("gkd kernel 2: canonical encode + mix");
-    CK(launch_encode((const BatchGenome *)c->batch_genomes.p, plan.n_genomes, tiles, c->cfg.alphabet, c->k, c->mix,
-                     plan.keys_a, c->stream));
-    nvtxRangePop();
-    if (tiles) c->m.launches++;
-    CK(cudaEventRecord(c->ev[1], c->stream));
     c->m.keys_sorted += raw;
-    rc = sort_and_finish(c, bg, ids, plan, tiles);  // records ev[2] between the sort and the unique / bin-sort stage
-    if (rc) return rc;
+    bool done = false;
+    if (msd_applies(c)) {
+        // fast path: kernel 2 writes straight into the bins of kernel 3 (ev[1] == ev[2]: the partition is part of
+        // the encode time, the bin sort is reported as unique_ms)
+        rc = build_batch_msd(c, bg, ids, tiles, nullptr, &done);
+        if (rc) return rc;
+        plan.keys_b = (uint64_t *)c->keys_b.p;  // the bin buffer may have been re-allocated larger
+    }
+    if (!done) {
+        nvtxRangePushA("gkd kernel 2: canonical encode + mix");
+        CK(launch_encode((const BatchGenome *)c->batch_genomes.p, plan.n_genomes, tiles, c->cfg.alphabet, c->k, c->mix,
+                         plan.keys_a, c->stream));
+        nvtxRangePop();
+        if (tiles) c->m.launches++;
+        CK(cudaEventRecord(c->ev[1], c->stream));
+        rc = sort_and_finish_lsd(c, bg, ids, plan);
+        if (rc) return rc;
+    }
     CK(cudaEventRecord(c->ev[3], c->stream));
     CK(cudaStreamSynchronize(c->stream));
     c->m.encode_ms += elapsed(c->ev[0], c->ev[1]);
@@ -753,7 +775,13 @@ int import_device_batch(gkd_ctx *c, const uint64_t *keys, const uint64_t *offset
         c->m.launches++;
     }
     for (uint32_t i = i0; i < i1; i++) c->genomes.push_back(GenomeRec());
-    rc = sort_and_finish(c, bg, ids, plan, tiles);
+    bool done = false;
+    rc = GKD_OK;
+    if (msd_applies(c)) {
+        rc = build_batch_msd(c, bg, ids, tiles, plan.keys_a, &done);
+        plan.keys_b = (uint64_t *)c->keys_b.p;  // the bin buffer may have been re-allocated larger
+    }
+    if (!rc && !done) rc = sort_and_finish_lsd(c, bg, ids, plan);
     if (rc) c->genomes.resize(id0);
     return rc;
 }

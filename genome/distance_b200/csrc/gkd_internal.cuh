@@ -195,32 +195,38 @@ struct SetBuild {
 };
 cudaError_t launch_unique_write(const BatchGenome *genomes, const SortPlan &plan, const uint64_t *sorted,
                                 const SetBuild *dst, int alphabet, int k, MixParams mix, int low_bits, cudaStream_t s);
-// kernel 3, fast path (sort_msd.cu): MSD partition by the top bits of h + one in-shared-memory sort per bin
-constexpr uint32_t MSD_BIN_AVG = 4096;  // a genome gets 2^p bins, p smallest with n_slots <= MSD_BIN_AVG << p
-constexpr uint32_t MSD_BIN_CAP = 5120;  // keys a bin-sort CTA holds; a fuller bin sends the batch to the LSD path
-constexpr uint32_t MSD_MAX_P = 12, MSD_SORT_BITS = 9, MSD_MAX_S = 12;
+// kernel 3, fast path (sort_msd.cu): MSD partition by the top bits of h fused into kernel 2 + one
+// in-shared-memory sort per bin
+constexpr uint32_t MSD_BIN_AVG = 8192;  // a genome gets 2^p bins, p smallest with n_slots <= MSD_BIN_AVG << p
+constexpr uint32_t MSD_BIN_CAP = 9024;  // most keys a bin region / a bin-sort CTA holds (8192 + 8 sigma + 64, rounded)
+constexpr uint32_t MSD_MAX_P = 12, MSD_SORT_BITS = 12;  // 4096 sort-buckets per bin: ~1-2 keys each
 struct MsdGenome {
     uint32_t bin_first;  // index of the genome's first bin in the batch bin arrays
     uint32_t p;          // bin bits
-    uint32_t s;          // sort-bucket bits inside a bin (p + s >= level)
+    uint32_t s;          // sort-bucket bits inside a bin
     uint32_t level;      // table level of the finished set (>= p)
+    uint32_t cap;        // keys a bin region of this genome holds
+    uint32_t pad_;
+    uint64_t bins_off;   // offset (keys) of the genome's bin 0 in the bin buffer; bin b starts at bins_off + b * cap
     void *lows;          // arena destinations
     uint32_t *offs;
 };
 struct MsdPlan {
-    uint32_t n_bins, max_p, max_s;
+    uint32_t n_bins, max_p;
     int key_bits;
-    const uint64_t *keys_in;  // h per slot (KEY_SENTINEL = invalid)
-    uint64_t *keys_out;       // the same keys grouped by bin
-    uint32_t *bin_count, *bin_cursor;
-    uint64_t *bin_start;
-    unsigned long long *status;
-    uint32_t *genome_valid, *genome_maxbin, *genome_unique;
+    uint64_t *bins;            // fixed-capacity bin regions
+    uint32_t *bin_cursor;      // [n_bins] keys in every bin
+    unsigned long long *status;  // [n_bins] look-back descriptors
+    uint32_t *genome_valid, *genome_maxbin, *genome_unique, *overflow;
 };
 cudaError_t msd_configure();
-cudaError_t launch_msd_partition(const BatchGenome *genomes, uint32_t n_genomes, uint32_t n_tiles, const MsdGenome *msd,
-                                 const MsdPlan &plan, cudaStream_t s);
-cudaError_t launch_msd_binsort(const MsdGenome *msd, uint32_t n_genomes, const MsdPlan &plan, int low_bits, cudaStream_t s);
+// keys_in == nullptr: encode the genomes (kernel 2) straight into the bins; else partition the given keys
+cudaError_t launch_encode_scatter(const BatchGenome *genomes, uint32_t n_genomes, uint32_t n_tiles, const MsdGenome *msd,
+                                  uint32_t max_p, int alphabet, int k, MixParams mix, const uint64_t *keys_in, uint64_t *bins_out,
+                                  uint32_t *bin_cursor, uint32_t *overflow, cudaStream_t s);
+cudaError_t launch_msd_totals(const MsdGenome *msd, uint32_t n_genomes, const MsdPlan &plan, cudaStream_t s);
+cudaError_t launch_msd_binsort(const MsdGenome *msd, uint32_t n_genomes, const MsdPlan &plan, int low_bits, bool narrow,
+                               cudaStream_t s);
 // in-place key -> h for imported key arrays (keys outside the key space become KEY_SENTINEL)
 cudaError_t launch_mix_keys(uint64_t *keys, uint64_t n, MixParams mix, cudaStream_t s);
 // bucketed set -> original keys (unsorted: ascending h order), for export

@@ -121,6 +121,63 @@ cudaError_t launch_pack_prot(const char *text, uint64_t n_pos, uint8_t *codes, u
 // ------------------------------------------------------------------------------------------------
 constexpr int ENC_STRIDE = ENC_PER_THREAD + 1;  // smem padding: conflict-free 64-bit stores
 
+// The ENC_PER_THREAD k-mer slots that start at stream position my0: emit(j, h) receives h = mix(key) of slot
+// my0 + j, or KEY_SENTINEL when the window holds an invalid position / runs past the genome.  j is a
+// compile-time index in every call, so callers may keep the keys in registers.
+template <int ALPHA, class Emit>
+__device__ __forceinline__ void encode_thread(const BatchGenome &G, int k, const MixParams &mix, uint32_t my0, Emit emit) {
+    const uint32_t w0 = my0 / PACK_POS_PER_WORD;
+    const uint32_t off = my0 % PACK_POS_PER_WORD;  // 0 or 16
+    // invalid bits for relative positions 0..47
+    const uint64_t inv = (((uint64_t)__ldg(G.mask + w0 + 1) << 32) | __ldg(G.mask + w0)) >> off;
+    const uint64_t kbits = (k >= 64) ? ~0ull : ((1ull << k) - 1);
+    if (ALPHA == GKD_PROT) {
+        const uint64_t kmask = (k >= 8) ? ~0ull : ((1ull << (8 * k)) - 1);
+        const uint8_t *bytes = reinterpret_cast<const uint8_t *>(G.codes) + my0;
+        // 16 slots need bytes [0, 16 + k - 1) <= 23: three aligned 8-byte loads
+        const uint64_t *q = reinterpret_cast<const uint64_t *>(bytes);
+        const uint64_t b0 = __ldg(q), b1 = __ldg(q + 1), b2 = __ldg(q + 2);
+        auto byte_at = [&](int r) { return (uint64_t)((uint32_t)((r < 8 ? b0 : (r < 16 ? b1 : b2)) >> (8 * (r & 7))) & 0xFFu); };
+        uint64_t key = 0;
+        for (int r = 0; r < k - 1; r++) key = ((key << 8) | byte_at(r)) & kmask;  // first k-1 bytes of slot 0
+#pragma unroll
+        for (int j = 0; j < ENC_PER_THREAD; j++) {
+            key = ((key << 8) | byte_at(j + k - 1)) & kmask;  // key = bytes [j, j + k)
+            const bool ok = ((inv >> j) & kbits) == 0 && (my0 + j) < G.n_slots;
+            emit(j, ok ? mix_key(key, mix) : KEY_SENTINEL);
+        }
+    } else {
+        const uint64_t kmask = (k >= 32) ? ~0ull : ((1ull << (2 * k)) - 1);
+        const int top = 2 * (k - 1);
+        const uint64_t *cw = G.codes + w0;
+        const uint64_t c0 = __ldg(cw), c1 = __ldg(cw + 1);
+        uint64_t lo, hi;  // 128-bit little-endian window starting at this thread's first base
+        if (off) {
+            lo = (c0 >> (2 * off)) | (c1 << (64 - 2 * off));
+            hi = c1 >> (2 * off);
+        } else {
+            lo = c0;
+            hi = c1;
+        }
+        // v = the K bases as stored (first base least significant): as a number that is the
+        // REVERSED k-mer, so the reverse-complement key is simply its complement.
+        uint64_t v = lo & kmask;
+        uint64_t fwd = reverse_pairs(v) >> (64 - 2 * k);
+#pragma unroll
+        for (int j = 0; j < ENC_PER_THREAD; j++) {
+            const uint64_t rc = (~v) & kmask;
+            const uint64_t key = fwd < rc ? fwd : rc;
+            const bool ok = ((inv >> j) & kbits) == 0 && (my0 + j) < G.n_slots;
+            emit(j, ok ? mix_key(key, mix) : KEY_SENTINEL);  // sets are kept in mixed-key order
+            // slide one base: the 128-bit window shifts right by one code
+            lo = (lo >> 2) | (hi << 62);
+            hi >>= 2;
+            v = lo & kmask;
+            fwd = ((fwd << 2) | ((v >> top) & 3ull)) & kmask;
+        }
+    }
+}
+
 template <int ALPHA>
 __global__ void __launch_bounds__(ENC_THREADS)
     k_encode(const BatchGenome *__restrict__ genomes, uint32_t n_genomes, int k, MixParams mix,
@@ -134,62 +191,7 @@ __global__ void __launch_bounds__(ENC_THREADS)
     const uint32_t slot0 = tile * ENC_TILE;                    // first slot of this tile
     const uint32_t my0 = slot0 + threadIdx.x * ENC_PER_THREAD;  // first slot of this thread
     uint64_t *mine = stage + threadIdx.x * ENC_STRIDE;
-
-    if (my0 < G.n_slots) {
-        const uint32_t w0 = my0 / PACK_POS_PER_WORD;
-        const uint32_t off = my0 % PACK_POS_PER_WORD;  // 0 or 16
-        // invalid bits for relative positions 0..47
-        uint64_t inv = (((uint64_t)__ldg(G.mask + w0 + 1) << 32) | __ldg(G.mask + w0)) >> off;
-        const uint64_t kbits = (k >= 64) ? ~0ull : ((1ull << k) - 1);
-        if (ALPHA == GKD_PROT) {
-            const uint64_t kmask = (k >= 8) ? ~0ull : ((1ull << (8 * k)) - 1);
-            const uint8_t *bytes = reinterpret_cast<const uint8_t *>(G.codes) + my0;
-            // 16 slots need bytes [0, 16 + k - 1) <= 23: three aligned 8-byte loads
-            const uint64_t *q = reinterpret_cast<const uint64_t *>(bytes);
-            uint64_t b0 = __ldg(q), b1 = __ldg(q + 1), b2 = __ldg(q + 2);
-            uint64_t key = 0;
-#pragma unroll
-            for (int r = 0; r < ENC_PER_THREAD + 7; r++) {
-                uint64_t word = r < 8 ? b0 : (r < 16 ? b1 : b2);
-                uint32_t c = (uint32_t)(word >> (8 * (r & 7))) & 0xFFu;
-                key = ((key << 8) | c) & kmask;
-                int j = r - (k - 1);  // slot completed by this byte
-                if (j >= 0 && j < ENC_PER_THREAD) {
-                    bool ok = ((inv >> j) & kbits) == 0 && (my0 + j) < G.n_slots;
-                    mine[j] = ok ? mix_key(key, mix) : KEY_SENTINEL;
-                }
-            }
-        } else {
-            const uint64_t kmask = (k >= 32) ? ~0ull : ((1ull << (2 * k)) - 1);
-            const int top = 2 * (k - 1);
-            const uint64_t *cw = G.codes + w0;
-            uint64_t c0 = __ldg(cw), c1 = __ldg(cw + 1);
-            uint64_t lo, hi;  // 128-bit little-endian window starting at this thread's first base
-            if (off) {
-                lo = (c0 >> (2 * off)) | (c1 << (64 - 2 * off));
-                hi = c1 >> (2 * off);
-            } else {
-                lo = c0;
-                hi = c1;
-            }
-            // v = the K bases as stored (first base least significant): as a number that is the
-            // REVERSED k-mer, so the reverse-complement key is simply its complement.
-            uint64_t v = lo & kmask;
-            uint64_t fwd = reverse_pairs(v) >> (64 - 2 * k);
-#pragma unroll
-            for (int j = 0; j < ENC_PER_THREAD; j++) {
-                uint64_t rc = (~v) & kmask;
-                uint64_t key = fwd < rc ? fwd : rc;
-                bool ok = ((inv >> j) & kbits) == 0 && (my0 + j) < G.n_slots;
-                mine[j] = ok ? mix_key(key, mix) : KEY_SENTINEL;  // sets are kept in mixed-key order
-                // slide one base: the 128-bit window shifts right by one code
-                lo = (lo >> 2) | (hi << 62);
-                hi >>= 2;
-                v = lo & kmask;
-                fwd = ((fwd << 2) | ((v >> top) & 3ull)) & kmask;
-            }
-        }
-    }
+    if (my0 < G.n_slots) encode_thread<ALPHA>(G, k, mix, my0, [&](int j, uint64_t h) { mine[j] = h; });
     __syncthreads();
     // coalesced write-out of the tile
     const uint32_t remaining = G.n_slots > slot0 ? G.n_slots - slot0 : 0;
@@ -200,11 +202,133 @@ __global__ void __launch_bounds__(ENC_THREADS)
         dst[idx] = stage[(idx / ENC_PER_THREAD) * ENC_STRIDE + (idx % ENC_PER_THREAD)];
 }
 
+// ---- kernel 2 fused with the MSD partition of kernel 3 (sort_msd.cu) --------------------------------------
+// The mixed keys are uniform, so a genome's bins (top p bits of h) have predictable sizes and get FIXED
+// capacity regions: no histogram pass, no scan.  The keys stay in registers; a tile ranks them by bin with
+// shared-memory atomics, reserves room in every bin with one global atomic per (tile, bin) and writes each key
+// straight to its bin.  A bin that would overflow (heavily repeated k-mers) raises *overflow and the host
+// re-runs the batch on the LSD path.
+template <int ALPHA>
+__global__ void __launch_bounds__(ENC_THREADS, 4)
+    k_encode_scatter(const BatchGenome *__restrict__ genomes, uint32_t n_genomes, const MsdGenome *__restrict__ msd, int k,
+                     MixParams mix, uint64_t *__restrict__ bins_out, uint32_t *__restrict__ bin_cursor,
+                     uint32_t *__restrict__ overflow) {
+    extern __shared__ uint32_t s_bin[];  // [2^p] keys of this tile per bin, then the reserved offset in the bin
+    __shared__ uint32_t s_g;
+    if (threadIdx.x == 0) s_g = find_genome(genomes, n_genomes, blockIdx.x);
+    __syncthreads();
+    const BatchGenome G = genomes[s_g];
+    const MsdGenome M = msd[s_g];
+    const uint32_t n_bins = 1u << M.p;
+    for (uint32_t i = threadIdx.x; i < n_bins; i += ENC_THREADS) s_bin[i] = 0;
+    __syncthreads();
+    const int shift = mix.bits - (int)M.p;
+    const uint32_t my0 = (blockIdx.x - G.tile_first) * ENC_TILE + threadIdx.x * ENC_PER_THREAD;
+    uint64_t key[ENC_PER_THREAD];
+    uint32_t rank[ENC_PER_THREAD];
+#pragma unroll
+    for (int j = 0; j < ENC_PER_THREAD; j++) key[j] = KEY_SENTINEL, rank[j] = 0;
+    if (my0 < G.n_slots)
+        encode_thread<ALPHA>(G, k, mix, my0, [&](int j, uint64_t h) {
+            key[j] = h;
+            if (h != KEY_SENTINEL) rank[j] = atomicAdd(&s_bin[M.p ? (uint32_t)(h >> shift) : 0u], 1u);
+        });
+    __syncthreads();
+    for (uint32_t b = threadIdx.x; b < n_bins; b += ENC_THREADS) {
+        const uint32_t v = s_bin[b];
+        if (v) {
+            uint32_t base = atomicAdd(&bin_cursor[M.bin_first + b], v);
+            if (base + v > M.cap) {
+                atomicExch(overflow, 1u);
+                base = 0xFFFFFFFFu;
+            }
+            s_bin[b] = base;
+        }
+    }
+    __syncthreads();
+    uint64_t *out = bins_out + M.bins_off;
+#pragma unroll
+    for (int j = 0; j < ENC_PER_THREAD; j++)
+        if (key[j] != KEY_SENTINEL) {
+            const uint32_t b = M.p ? (uint32_t)(key[j] >> shift) : 0u;
+            const uint32_t base = s_bin[b];
+            if (base != 0xFFFFFFFFu) out[(uint64_t)b * M.cap + base + rank[j]] = key[j];
+        }
+}
+
+// the same partition for keys that already exist (imported key arrays): in = h per slot
+__global__ void __launch_bounds__(ENC_THREADS)
+    k_keys_scatter(const BatchGenome *__restrict__ genomes, uint32_t n_genomes, const MsdGenome *__restrict__ msd, int key_bits,
+                   const uint64_t *__restrict__ in, uint64_t *__restrict__ bins_out, uint32_t *__restrict__ bin_cursor,
+                   uint32_t *__restrict__ overflow) {
+    extern __shared__ uint32_t s_bin[];
+    __shared__ uint32_t s_g;
+    if (threadIdx.x == 0) s_g = find_genome(genomes, n_genomes, blockIdx.x);
+    __syncthreads();
+    const BatchGenome G = genomes[s_g];
+    const MsdGenome M = msd[s_g];
+    const uint32_t n_bins = 1u << M.p;
+    for (uint32_t i = threadIdx.x; i < n_bins; i += ENC_THREADS) s_bin[i] = 0;
+    __syncthreads();
+    const int shift = key_bits - (int)M.p;
+    const uint32_t slot0 = (blockIdx.x - G.tile_first) * ENC_TILE;
+    const uint32_t count = min((uint32_t)ENC_TILE, G.n_slots - slot0);
+    const uint64_t *src = in + G.raw_off + slot0;
+    uint64_t key[ENC_PER_THREAD];
+    uint32_t rank[ENC_PER_THREAD];
+#pragma unroll
+    for (int j = 0; j < ENC_PER_THREAD; j++) {
+        const uint32_t idx = j * ENC_THREADS + threadIdx.x;
+        key[j] = idx < count ? src[idx] : KEY_SENTINEL;
+        rank[j] = 0;
+        if (key[j] != KEY_SENTINEL) rank[j] = atomicAdd(&s_bin[M.p ? (uint32_t)(key[j] >> shift) : 0u], 1u);
+    }
+    __syncthreads();
+    for (uint32_t b = threadIdx.x; b < n_bins; b += ENC_THREADS) {
+        const uint32_t v = s_bin[b];
+        if (v) {
+            uint32_t base = atomicAdd(&bin_cursor[M.bin_first + b], v);
+            if (base + v > M.cap) {
+                atomicExch(overflow, 1u);
+                base = 0xFFFFFFFFu;
+            }
+            s_bin[b] = base;
+        }
+    }
+    __syncthreads();
+    uint64_t *out = bins_out + M.bins_off;
+#pragma unroll
+    for (int j = 0; j < ENC_PER_THREAD; j++)
+        if (key[j] != KEY_SENTINEL) {
+            const uint32_t b = M.p ? (uint32_t)(key[j] >> shift) : 0u;
+            const uint32_t base = s_bin[b];
+            if (base != 0xFFFFFFFFu) out[(uint64_t)b * M.cap + base + rank[j]] = key[j];
+        }
+}
+
 cudaError_t launch_encode(const BatchGenome *genomes, uint32_t n_genomes, uint32_t n_tiles, int alphabet, int k,
                           MixParams mix, uint64_t *keys_out, cudaStream_t s) {
     if (n_tiles == 0) return cudaSuccess;
     if (alphabet == GKD_PROT) k_encode<GKD_PROT><<<n_tiles, ENC_THREADS, 0, s>>>(genomes, n_genomes, k, mix, keys_out);
     else k_encode<GKD_DNA><<<n_tiles, ENC_THREADS, 0, s>>>(genomes, n_genomes, k, mix, keys_out);
+    return cudaGetLastError();
+}
+
+}  // namespace gkd
+
+namespace gkd {
+
+cudaError_t launch_encode_scatter(const BatchGenome *genomes, uint32_t n_genomes, uint32_t n_tiles, const MsdGenome *msd,
+                                  uint32_t max_p, int alphabet, int k, MixParams mix, const uint64_t *keys_in, uint64_t *bins_out,
+                                  uint32_t *bin_cursor, uint32_t *overflow, cudaStream_t s) {
+    if (n_tiles == 0) return cudaSuccess;
+    const uint32_t smem = (1u << max_p) * 4;
+    if (keys_in)
+        k_keys_scatter<<<n_tiles, ENC_THREADS, smem, s>>>(genomes, n_genomes, msd, mix.bits, keys_in, bins_out, bin_cursor, overflow);
+    else if (alphabet == GKD_PROT)
+        k_encode_scatter<GKD_PROT><<<n_tiles, ENC_THREADS, smem, s>>>(genomes, n_genomes, msd, k, mix, bins_out, bin_cursor, overflow);
+    else
+        k_encode_scatter<GKD_DNA><<<n_tiles, ENC_THREADS, smem, s>>>(genomes, n_genomes, msd, k, mix, bins_out, bin_cursor, overflow);
     return cudaGetLastError();
 }
 
