@@ -89,6 +89,7 @@ SYMBOLS = {
     "gkd_all_vs_all_range_ex": (_i32, [_vp, _u32, _u64, _u64, C.POINTER(GkdOutputs)]),
     "gkd_query_vs_ref_ex": (_i32, [_vp, _vp, _u32, _vp, _u32, C.POINTER(GkdOutputs)]),
     "gkd_pairs_ex": (_i32, [_vp, _vp, _vp, _u64, C.POINTER(GkdOutputs)]),
+    "gkd_greedy_reps": (_i32, [_vp, _vp, _u32, _dbl, _vp]),
     "gkd_pair": (_i32, [_vp, _u32, _u32, _pu64, _pu64, _pdbl]),
     "gkd_hash_set": (_i32, [_vp, _u32, _u32, _i32, _vp, _pu32]),
     "gkd_sketch_distances": (_i32, [_vp, _u32, _i32, _vp, _vp, _u64, _vp]),

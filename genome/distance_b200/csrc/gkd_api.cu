@@ -113,6 +113,7 @@ struct gkd_ctx {
     DevBuf d_sets, counts, pal_counts, d_inter, d_dist, d_ca, d_cb, ids_a, ids_b, work_counter;
     DevBuf sk_cand, sk_misc, sk_sig, sk_len, sk_out;
     DevBuf msd_genomes, msd_bins32, msd_bins64, msd_gstat;
+    DevBuf gr_reps, gr_flags;
     bool use_msd = true;  // GKD_SORT_ALGO=lsd pins the LSD path
     bool sets_dirty = true;
 
@@ -1179,7 +1180,8 @@ int gkd_destroy(gkd_ctx *c) {
     DevBuf *bufs[] = {&c->keys_a, &c->keys_b, &c->tile_hist, &c->tile_uniq, &c->genome_counts, &c->batch_genomes,
                       &c->set_build, &c->d_sets, &c->counts, &c->pal_counts, &c->d_inter, &c->d_dist, &c->d_ca,
                       &c->d_cb, &c->ids_a, &c->ids_b, &c->work_counter, &c->sk_cand, &c->sk_misc, &c->sk_sig,
-                      &c->sk_len, &c->sk_out, &c->msd_genomes, &c->msd_bins32, &c->msd_bins64, &c->msd_gstat};
+                      &c->sk_len, &c->sk_out, &c->msd_genomes, &c->msd_bins32, &c->msd_bins64, &c->msd_gstat,
+                      &c->gr_reps, &c->gr_flags};
     for (DevBuf *b : bufs)
         if (b->p) cudaFreeAsync(b->p, c->stream);
     cudaStreamSynchronize(c->stream);
@@ -1633,6 +1635,110 @@ int gkd_pairs_ex(gkd_ctx *c, const uint32_t *a, const uint32_t *b, uint64_t n_pa
 int gkd_pairs(gkd_ctx *c, const uint32_t *a, const uint32_t *b, uint64_t n_pairs, uint64_t *inter, double *dist) {
     gkd_outputs o{inter, dist, nullptr, nullptr};
     return gkd_pairs_ex(c, a, b, n_pairs, &o);
+}
+
+int gkd_greedy_reps(gkd_ctx *c, const uint32_t *order, uint32_t n, double max_dist, uint8_t *is_rep) {
+    CHECK_CTX(c);
+    if (n == 0) return GKD_OK;
+    if (!order || !is_rep) return fail(c, GKD_EINVAL, "gkd_greedy_reps: null argument");
+    CK(cudaSetDevice(c->cfg.device));
+    ABI_GUARD_BEGIN
+    int rc = upload_sets(c);
+    if (rc) return rc;
+    const bool nuc = c->cfg.alphabet != GKD_PROT;
+    const bool both = nuc && c->cfg.strand_mode == GKD_STRAND_BOTH;
+    const bool need_pal = both && (c->k % 2 == 0);
+    uint64_t max_n = 0, max_pal = 0;
+    uint32_t max_level = 0, max_pal_level = 0;
+    bool any_lit = false;
+    for (uint32_t i = 0; i < n; i++) {
+        if ((rc = check_built(c, order[i]))) return rc;
+        const GenomeRec &g = c->genomes[order[i]];
+        max_n = std::max<uint64_t>(max_n, g.desc.main.n);
+        max_pal = std::max<uint64_t>(max_pal, g.desc.pal.n);
+        max_level = std::max(max_level, g.desc.main.level);
+        max_pal_level = std::max(max_pal_level, g.desc.pal.level);
+        any_lit = any_lit || !g.lit.empty();
+    }
+    if (any_lit) {
+        // literal ambiguous k-mers are completed on the host: one batched call per candidate
+        std::vector<uint32_t> reps, cand;
+        std::vector<double> dist;
+        for (uint32_t i = 0; i < n; i++) {
+            bool found = false;
+            if (!reps.empty()) {
+                cand.assign(reps.size(), order[i]);
+                dist.assign(reps.size(), 1.0);
+                gkd_outputs o{nullptr, dist.data(), nullptr, nullptr};
+                HostPairs hp{PAIRS_LIST, 0, 0, reps.size(), reps.data(), cand.data(), (uint32_t)reps.size(), (uint32_t)reps.size()};
+                if ((rc = run_pairs(c, hp, o))) return rc;
+                for (double d : dist) found = found || d <= max_dist;
+            }
+            is_rep[i] = found ? 0 : 1;
+            if (!found) reps.push_back(order[i]);
+        }
+        return GKD_OK;
+    }
+    // device state: representative ids, their count, per-visit flags, counts (zeroed once; the decision kernel
+    // clears what it consumed)
+    if ((rc = ensure(c, c->gr_reps, (uint64_t)n * 4 + 16))) return rc;
+    if ((rc = ensure(c, c->gr_flags, (uint64_t)n))) return rc;
+    if ((rc = ensure(c, c->counts, (uint64_t)n * 4))) return rc;
+    if (need_pal && (rc = ensure(c, c->pal_counts, (uint64_t)n * 4))) return rc;
+    if ((rc = ensure(c, c->work_counter, 8))) return rc;
+    uint32_t *d_reps = (uint32_t *)c->gr_reps.p, *d_nreps = d_reps + n;
+    CK(cudaMemsetAsync(d_nreps, 0, 16, c->stream));
+    CK(cudaMemsetAsync(c->counts.p, 0, (uint64_t)n * 4, c->stream));
+    if (need_pal) CK(cudaMemsetAsync(c->pal_counts.p, 0, (uint64_t)n * 4, c->stream));
+    const uint64_t warps = (uint64_t)c->n_sms * intersect_warps_per_sm(c->low_bits);
+    auto plan_for = [&](uint64_t nmax, uint32_t lmax, uint64_t pairs, bool one_item) {
+        IsectPlan p{};
+        p.low_bits = c->low_bits;
+        p.tmax = c->isect_tmax;
+        p.level_min = c->lvl_min;
+        uint32_t L = std::min(std::max(level_for((uint32_t)nmax, p.tmax), c->lvl_min), lmax);
+        const uint64_t max_groups = ((1ull << L) + 31) >> 5;
+        uint64_t gpi = max_groups;
+        if (!one_item && max_groups > 64)
+            gpi = (uint64_t)std::min<long double>((long double)pairs * max_groups / (long double)(warps * 8), (long double)(max_groups / 8));
+        gpi = std::min<uint64_t>(std::max<uint64_t>(gpi, 1), max_groups);
+        p.groups_per_item = (uint32_t)gpi;
+        p.items_per_pair = (uint32_t)((max_groups + gpi - 1) / gpi);
+        return p;
+    };
+    CK(cudaEventRecord(c->ev[4], c->stream));
+    NvtxRange nvtx("gkd greedy representatives (kernels 4+5 per candidate, device-resident list)");
+    for (uint32_t i = 0; i < n; i++) {
+        if (i > 0) {  // at most i representatives so far
+            PairSource src{};
+            src.mode = PAIRS_LIST_VS_ONE;
+            src.n = order[i];
+            src.count = i;
+            src.a = d_reps;
+            src.count_ptr = d_nreps;
+            CK(launch_intersect((const SetDesc *)c->d_sets.p, src, 0, plan_for(max_n, max_level, i, false), (uint32_t *)c->counts.p,
+                                (unsigned long long *)c->work_counter.p, c->n_sms, c->stream));
+            c->m.launches++;
+            c->m.intersect_launches++;
+            if (need_pal && max_pal) {
+                CK(launch_intersect((const SetDesc *)c->d_sets.p, src, 1, plan_for(max_pal, max_pal_level, i, true),
+                                    (uint32_t *)c->pal_counts.p, (unsigned long long *)c->work_counter.p, c->n_sms, c->stream));
+                c->m.launches++;
+            }
+        }
+        CK(launch_greedy_decide((const SetDesc *)c->d_sets.p, d_reps, d_nreps, order[i], i, (uint32_t *)c->counts.p,
+                                need_pal ? (uint32_t *)c->pal_counts.p : nullptr, both ? 1 : 0, max_dist,
+                                (uint8_t *)c->gr_flags.p, c->stream));
+        c->m.launches++;
+    }
+    CK(cudaEventRecord(c->ev[5], c->stream));
+    CK(cudaMemcpyAsync(is_rep, c->gr_flags.p, n, cudaMemcpyDefault, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    c->m.d2h_bytes += n;
+    c->m.intersect_ms = elapsed(c->ev[4], c->ev[5]);
+    c->m.total_intersect_ms += c->m.intersect_ms;
+    return GKD_OK;
+    ABI_GUARD_END(c)
 }
 
 int gkd_pair(gkd_ctx *c, uint32_t a, uint32_t b, uint64_t *inter, uint64_t *uni, double *dist) {

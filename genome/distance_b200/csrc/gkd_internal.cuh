@@ -149,15 +149,16 @@ struct BatchGenome {
 };
 
 // Pair enumeration modes of the intersect kernel
-enum PairMode : int { PAIRS_LIST = 0, PAIRS_UPPER = 1, PAIRS_RECT = 2 };
+enum PairMode : int { PAIRS_LIST = 0, PAIRS_UPPER = 1, PAIRS_RECT = 2, PAIRS_LIST_VS_ONE = 3 };
 
 struct PairSource {
     int mode;
-    uint32_t n;          // UPPER: number of sets; RECT: number of refs (columns)
+    uint32_t n;          // UPPER: number of sets; RECT: number of refs (columns); LIST_VS_ONE: the one set id
     uint64_t first;      // UPPER: linear index of the first pair of this call
-    uint64_t count;      // pairs in this call
-    const uint32_t *a;   // LIST: a ids; RECT: query ids; UPPER: nullptr (ids are 0..n-1)
+    uint64_t count;      // pairs in this call (an upper bound when count_ptr is set)
+    const uint32_t *a;   // LIST / LIST_VS_ONE: a ids; RECT: query ids; UPPER: nullptr (ids are 0..n-1)
     const uint32_t *b;   // LIST: b ids; RECT: ref ids
+    const uint32_t *count_ptr;  // device-resident pair count (greedy pass: the list grows on the device), or nullptr
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -253,6 +254,11 @@ struct EpilogueOut {
 };
 cudaError_t launch_epilogue(const SetDesc *sets, PairSource src, const uint32_t *counts, const uint32_t *pal_counts,
                             int both_strands, EpilogueOut out, cudaStream_t s);
+// greedy representative pass, decision step: candidate `cand` (visit index `visit`) joins reps[0..*n_reps) unless
+// some representative is within max_dist; clears the counts it consumed
+cudaError_t launch_greedy_decide(const SetDesc *sets, uint32_t *reps, uint32_t *n_reps, uint32_t cand, uint32_t visit,
+                                 uint32_t *counts, uint32_t *pal_counts, int both_strands, double max_dist, uint8_t *is_rep,
+                                 cudaStream_t s);
 // MinHash sketches (sketch.cu)
 constexpr uint32_t SKETCH_CAP = 32768;        // candidate codes one CTA sorts in shared memory
 constexpr uint32_t SKETCH_MAX_WIDTH = 4096;   // widest signature (the reference's commands use 360 and 2000)

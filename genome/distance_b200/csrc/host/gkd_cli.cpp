@@ -20,6 +20,7 @@
 #include <fstream>
 #include <iostream>
 #include <map>
+#include <set>
 #include <sstream>
 
 #include "kmers.hpp"
@@ -317,33 +318,54 @@ int fastaReps(const std::vector<std::string> &args) {
     // replaces the earlier one (HashMap.put, :145).
     writer << "seq\tname\n";
     std::vector<std::pair<std::string, uint32_t>> repMap;  // insertion-ordered label -> set handle
-    std::vector<uint32_t> a, b;
-    std::vector<double> dist;
     size_t pairCount = 0;
-    for (auto &seq : seqs) {
-        bool repFound = false;
-        if (!repMap.empty()) {
-            a.clear();
-            b.clear();
-            for (auto &r : repMap) {
-                a.push_back(r.second);        // repKmers.distance(seqKmers) (:128)
-                b.push_back(seq.handle());
+    bool uniqueLabels = true;
+    {
+        std::set<std::string> seen;
+        for (auto &seq : seqs) uniqueLabels = seen.insert(seq.getGenomeId()).second && uniqueLabels;
+    }
+    if (uniqueLabels) {
+        // the whole greedy pass on the device (gkd_greedy_reps): the representative list never leaves HBM and no
+        // candidate costs a host round trip
+        std::vector<uint32_t> order;
+        for (auto &seq : seqs) order.push_back(seq.handle());
+        std::vector<uint8_t> isRep(order.size(), 0);
+        engine.check(gkd_greedy_reps(engine.raw(), order.data(), (uint32_t)order.size(), maxDist, isRep.data()));
+        for (size_t i = 0; i < seqs.size(); i++)
+            if (isRep[i]) {
+                writer << seqs[i].getGenomeId() << '\t' << seqs[i].getGenomeName() << '\n';
+                repMap.emplace_back(seqs[i].getGenomeId(), seqs[i].handle());
             }
-            dist.assign(a.size(), 1.0);
-            engine.check(gkd_pairs(engine.raw(), a.data(), b.data(), a.size(), nullptr, dist.data()));
-            pairCount += a.size();
-            for (double d : dist)
-                if (d <= maxDist) repFound = true;
-        }
-        if (!repFound) {
-            writer << seq.getGenomeId() << '\t' << seq.getGenomeName() << '\n';
-            bool replaced = false;
-            for (auto &r : repMap)
-                if (r.first == seq.getGenomeId()) {
-                    r.second = seq.handle();
-                    replaced = true;
+    } else {
+        // duplicate labels: a later representative replaces the earlier one under the same key (HashMap.put,
+        // :145), which changes who is compared -- keep the literal per-candidate loop for that case
+        std::vector<uint32_t> a, b;
+        std::vector<double> dist;
+        for (auto &seq : seqs) {
+            bool repFound = false;
+            if (!repMap.empty()) {
+                a.clear();
+                b.clear();
+                for (auto &r : repMap) {
+                    a.push_back(r.second);        // repKmers.distance(seqKmers) (:128)
+                    b.push_back(seq.handle());
                 }
-            if (!replaced) repMap.emplace_back(seq.getGenomeId(), seq.handle());
+                dist.assign(a.size(), 1.0);
+                engine.check(gkd_pairs(engine.raw(), a.data(), b.data(), a.size(), nullptr, dist.data()));
+                pairCount += a.size();
+                for (double d : dist)
+                    if (d <= maxDist) repFound = true;
+            }
+            if (!repFound) {
+                writer << seq.getGenomeId() << '\t' << seq.getGenomeName() << '\n';
+                bool replaced = false;
+                for (auto &r : repMap)
+                    if (r.first == seq.getGenomeId()) {
+                        r.second = seq.handle();
+                        replaced = true;
+                    }
+                if (!replaced) repMap.emplace_back(seq.getGenomeId(), seq.handle());
+            }
         }
     }
     writer.flush();
@@ -607,7 +629,22 @@ int distReps(const std::vector<std::string> &args) {
     if (maxDist <= 0.0 || maxDist >= 1.0) throw ParseFailureException("Distance must be strictly between 0 and 1.");
     for (auto &d : p.positional)
         if (!exists(d)) throw IOException("Genome source " + d + " is not found.");
-    if (!isDir(outDir) && mkdir(outDir.c_str(), 0777) != 0) throw IOException("Cannot create output directory " + outDir + ".");
+    if (!isDir(outDir)) {
+        if (mkdir(outDir.c_str(), 0777) != 0) throw IOException("Cannot create output directory " + outDir + ".");
+    } else if (p.values.count("--clear")) {
+        // BaseMultiReportProcessor erases the output directory before processing when --clear is given
+        logInfo("Erasing output directory " + outDir + ".");
+        if (DIR *d = opendir(outDir.c_str())) {
+            while (dirent *e = readdir(d)) {
+                const std::string name = e->d_name;
+                if (name == "." || name == "..") continue;
+                const std::string path = outDir + "/" + name;
+                struct stat st;
+                if (stat(path.c_str(), &st) == 0 && S_ISREG(st.st_mode)) remove(path.c_str());
+            }
+            closedir(d);
+        }
+    }
 
     KmerEngine engine(KmerType::DNA, kmerSize, device);
     std::vector<SequenceKmers> all;
@@ -622,26 +659,19 @@ int distReps(const std::vector<std::string> &args) {
     logInfo("Starting first pass to find representatives.");
     std::vector<size_t> reps;            // indices into `all`, in insertion order
     std::vector<char> isRep(all.size(), 0);
-    std::vector<uint32_t> a, b;
-    std::vector<double> dist;
-    for (size_t i = 0; i < all.size(); i++) {
-        bool belongs = false;
-        if (!reps.empty()) {
-            a.clear();
-            b.clear();
-            for (size_t r : reps) {
-                a.push_back(all[r].handle());  // x.distance(kmers) (:190)
-                b.push_back(all[i].handle());
+    {
+        // x.distance(kmers) <= maxDist for any current representative x (:185-201), for every genome in turn, as one
+        // device-resident pass (gkd_greedy_reps)
+        std::vector<uint32_t> order;
+        for (auto &g : all) order.push_back(g.handle());
+        std::vector<uint8_t> flags(order.size(), 0);
+        if (!order.empty())
+            engine.check(gkd_greedy_reps(engine.raw(), order.data(), (uint32_t)order.size(), maxDist, flags.data()));
+        for (size_t i = 0; i < all.size(); i++)
+            if (flags[i]) {
+                reps.push_back(i);
+                isRep[i] = 1;
             }
-            dist.assign(a.size(), 1.0);
-            engine.check(gkd_pairs(engine.raw(), a.data(), b.data(), a.size(), nullptr, dist.data()));
-            for (double d : dist)
-                if (d <= maxDist) belongs = true;
-        }
-        if (!belongs) {
-            reps.push_back(i);
-            isRep[i] = 1;
-        }
     }
     logInfo(std::to_string(reps.size()) + " total representatives found for " + std::to_string(all.size()) + " genomes.");
     // pass 2: closest representative of every other genome in one batched call; ties keep the

@@ -100,6 +100,9 @@ __device__ __forceinline__ void decode_pair(const PairSource &src, uint64_t t, u
     } else if (src.mode == PAIRS_RECT) {
         ida = src.a[t / src.n];
         idb = src.b[t % src.n];
+    } else if (src.mode == PAIRS_LIST_VS_ONE) {
+        ida = src.a[t];
+        idb = src.n;
     } else {
         ida = src.a[t];
         idb = src.b[t];
@@ -248,7 +251,7 @@ __global__ void __launch_bounds__(C::WARPS * 32, C::CTAS)
     __syncwarp();
     uint32_t phases = 0;  // bit s = parity to wait for on the barrier of stage s
 
-    const uint64_t total_items = src.count * (uint64_t)plan.items_per_pair;
+    const uint64_t total_items = (src.count_ptr ? (uint64_t)*src.count_ptr : src.count) * (uint64_t)plan.items_per_pair;
     unsigned long long next_item = 0;
     if (lane == 0) next_item = atomicAdd(work_counter, 1ull);
     for (;;) {
@@ -434,20 +437,13 @@ cudaError_t launch_intersect(const SetDesc *sets, PairSource src, int use_pal, c
 }
 
 // ---- kernel 5: distance epilogue ----------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
-    k_epilogue(const SetDesc *__restrict__ sets, PairSource src, const uint32_t *__restrict__ counts,
-               const uint32_t *__restrict__ pal_counts, int both_strands, EpilogueOut out) {
-    uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= src.count) return;
-    uint32_t ida, idb;
-    decode_pair(src, t, ida, idb);
+// SequenceKmers.similarity / distance of one pair from the canonical counts (c = |C_A n C_B|, cp = palindromic part)
+__device__ __forceinline__ void pair_result(const SetDesc *__restrict__ sets, uint32_t ida, uint32_t idb, uint64_t c, uint64_t cp,
+                                            int both_strands, uint64_t &I, uint64_t &sa, uint64_t &sb, double &dist) {
     const uint32_t nA = sets[ida].main.n, nB = sets[idb].main.n;
     const uint32_t pA = sets[ida].pal.n, pB = sets[idb].pal.n;
-    uint64_t c = counts[t];
-    uint64_t I, sa, sb;
     if (both_strands) {
         // the reference's sets hold both strands: |S| = 2|C| - P, I = 2|C_A n C_B| - P(C_A n C_B)
-        uint64_t cp = pal_counts ? pal_counts[t] : 0;
         I = 2 * c - cp;
         sa = 2ull * nA - pA;
         sb = 2ull * nB - pB;
@@ -456,20 +452,69 @@ __global__ void __launch_bounds__(256)
         sa = nA;
         sb = nB;
     }
-    if (out.inter) out.inter[t] = I;
-    if (out.dist) {
-        double ret = 1.0;
-        double similarity = (double)I;
-        if (similarity > 0) {
-            // (this.size() + other.size()) is a Java int addition
-            int32_t sum = (int32_t)((uint32_t)sa + (uint32_t)sb);
-            double uni = (double)sum - similarity;
-            ret = 1.0 - similarity / uni;
-        }
-        out.dist[t] = ret;
+    dist = 1.0;
+    const double similarity = (double)I;
+    if (similarity > 0) {
+        // (this.size() + other.size()) is a Java int addition
+        const int32_t sum = (int32_t)((uint32_t)sa + (uint32_t)sb);
+        const double uni = (double)sum - similarity;
+        dist = 1.0 - similarity / uni;
     }
+}
+
+__global__ void __launch_bounds__(256)
+    k_epilogue(const SetDesc *__restrict__ sets, PairSource src, const uint32_t *__restrict__ counts,
+               const uint32_t *__restrict__ pal_counts, int both_strands, EpilogueOut out) {
+    uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= src.count) return;
+    uint32_t ida, idb;
+    decode_pair(src, t, ida, idb);
+    uint64_t I, sa, sb;
+    double d;
+    pair_result(sets, ida, idb, counts[t], pal_counts ? pal_counts[t] : 0, both_strands, I, sa, sb, d);
+    if (out.inter) out.inter[t] = I;
+    if (out.dist) out.dist[t] = d;
     if (out.contain_a) out.contain_a[t] = sa ? (double)I / (double)sa : 0.0;
     if (out.contain_b) out.contain_b[t] = sb ? (double)I / (double)sb : 0.0;
+}
+
+// Greedy representative pass (DistanceRepsProcessor.java:185-201, FastaDistanceRepsProcessor.java:124-146): the
+// candidate was intersected with every current representative (counts[t] for reps[t]); it joins the list unless
+// one of them is within max_dist.  The list and its length live on the device, so the host queues the launches
+// of every candidate back to back without reading anything.
+__global__ void __launch_bounds__(256)
+    k_greedy_decide(const SetDesc *__restrict__ sets, uint32_t *__restrict__ reps, uint32_t *__restrict__ n_reps, uint32_t cand,
+                    uint32_t visit, uint32_t *__restrict__ counts, uint32_t *__restrict__ pal_counts, int both_strands,
+                    double max_dist, uint8_t *__restrict__ is_rep) {
+    __shared__ int s_found;
+    if (threadIdx.x == 0) s_found = 0;
+    __syncthreads();
+    const uint32_t n = *n_reps;
+    int found = 0;
+    for (uint32_t t = threadIdx.x; t < n; t += blockDim.x) {
+        uint64_t I, sa, sb;
+        double d;
+        pair_result(sets, reps[t], cand, counts[t], pal_counts ? pal_counts[t] : 0, both_strands, I, sa, sb, d);
+        found |= d <= max_dist ? 1 : 0;
+        counts[t] = 0;  // ready for the next candidate
+        if (pal_counts) pal_counts[t] = 0;
+    }
+    if (found) atomicOr(&s_found, 1);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        is_rep[visit] = s_found ? 0 : 1;
+        if (!s_found) {
+            reps[n] = cand;
+            *n_reps = n + 1;
+        }
+    }
+}
+
+cudaError_t launch_greedy_decide(const SetDesc *sets, uint32_t *reps, uint32_t *n_reps, uint32_t cand, uint32_t visit,
+                                 uint32_t *counts, uint32_t *pal_counts, int both_strands, double max_dist, uint8_t *is_rep,
+                                 cudaStream_t s) {
+    k_greedy_decide<<<1, 256, 0, s>>>(sets, reps, n_reps, cand, visit, counts, pal_counts, both_strands, max_dist, is_rep);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_epilogue(const SetDesc *sets, PairSource src, const uint32_t *counts, const uint32_t *pal_counts,

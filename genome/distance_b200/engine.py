@@ -284,6 +284,13 @@ class Engine:
                                               dist.ctypes.data))
         return dist
 
+    def greedy_reps(self, order: Sequence[int], max_dist: float) -> np.ndarray:
+        """greedy representative pass on the device: flags[i] = 1 iff order[i] became a representative"""
+        o = np.ascontiguousarray(order, dtype=np.uint32)
+        flags = np.zeros(o.size, dtype=np.uint8)
+        self._ck(self._L.gkd_greedy_reps(self._h, o.ctypes.data, o.size, float(max_dist), flags.ctypes.data))
+        return flags
+
     def pair(self, a: int, b: int) -> Tuple[int, int, float]:
         i, u, d = C.c_uint64(), C.c_uint64(), C.c_double()
         self._ck(self._L.gkd_pair(self._h, a, b, C.byref(i), C.byref(u), C.byref(d)))

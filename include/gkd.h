@@ -207,6 +207,14 @@ int gkd_all_vs_all_range_ex(gkd_ctx *ctx, uint32_t n, uint64_t first, uint64_t c
 int gkd_query_vs_ref_ex(gkd_ctx *ctx, const uint32_t *q, uint32_t nq, const uint32_t *r, uint32_t nr,
                         const gkd_outputs *out);
 int gkd_pairs_ex(gkd_ctx *ctx, const uint32_t *a, const uint32_t *b, uint64_t n_pairs, const gkd_outputs *out);
+/* Greedy representative selection, pass 1 of DistanceRepsProcessor (:185-201) and the loop of
+ * FastaDistanceRepsProcessor (:117-147): the sets order[0..n) are visited in that order; a set becomes a
+ * representative unless some CURRENT representative is within max_dist (distance <= max_dist).  is_rep[i]
+ * receives 1 when order[i] became a representative, else 0.  The whole pass runs on the device: the
+ * representative list and its length stay in HBM and the launches of all candidates are queued back to back
+ * (no per-candidate id upload, result download or synchronisation).  Unlike the reference's anyMatch there is no
+ * early exit inside a candidate; the result is the same. */
+int gkd_greedy_reps(gkd_ctx *ctx, const uint32_t *order, uint32_t n, double max_dist, uint8_t *is_rep);
 /* SequenceKmers.distance(other) for one pair (DistanceRepsProcessor.java:101,190;
  * FastaDistanceRepsProcessor.java:128); uni = |A|+|B|-I */
 int gkd_pair(gkd_ctx *ctx, uint32_t a, uint32_t b, uint64_t *inter, uint64_t *uni, double *dist);

@@ -228,3 +228,9 @@ def test_distreps_matches_reference_greedy(orc, tmp_path):
     assert got == counts and 1 < len(reps) < len(order)
     sizes = [int(ln.split("\t")[2]) for ln in stats[1:]]
     assert sizes == sorted(sizes, reverse=True)
+    # --clear erases what an earlier run left in the output directory
+    (out_dir / "rep0.5000_K9.list.tbl").write_text("stale\n")
+    rc, out, err = run(["distReps", "-K", str(k), "--dist", str(max_dist), "-D", str(out_dir), "--clear", str(src)])
+    assert rc == 0, err
+    assert sorted(p.name for p in out_dir.iterdir()) == [prefix + ".list.tbl", prefix + ".stats.tbl"]
+    assert (out_dir / (prefix + ".list.tbl")).read_text().rstrip("\n").split("\n") == want_list

@@ -728,3 +728,30 @@ def test_both_kernel3_paths_build_identical_sets(orc, algo, monkeypatch):
             for i, p in enumerate(prots):
                 o = orc.IntSet(p, k, orc.PROT)
                 assert e.set_size(i)[1] == o.count and np.array_equal(e.export_set(i), o.keys()), (algo, k, i)
+
+
+@pytest.mark.parametrize("k,alpha", [(21, "DNA"), (12, "DNA"), (8, "PROT")])
+def test_greedy_representatives_on_device(orc, k, alpha):
+    """gkd_greedy_reps (pass 1 of DistanceRepsProcessor.java:185-201 / FastaDistanceRepsProcessor.java:124-146): the
+    device-resident greedy pass must pick exactly the representatives the literal loop over oracle distances picks,
+    for several thresholds and visiting orders (odd and even K, protein)."""
+    rng = random.Random(5150 + k)
+    letters = "ACDEFGHIKLMNPQRSTVWY" if alpha == "PROT" else "acgt"
+    al, oal = (gkd.PROT, orc.PROT) if alpha == "PROT" else (gkd.DNA, orc.DNA)
+    bases = [_rand_dna(rng, rng.randint(3000, 40000), letters) for _ in range(5)]
+    seqs = [_mutate(rng, bases[i % 5], 0.004 * (i // 5), letters) for i in range(40)] + ["", letters[:2]]
+    osets = [orc.IntSet(s, k, oal) for s in seqs]
+    with gkd.Engine(k=k, alphabet=al) as e:
+        for s in seqs:
+            e.add(s)
+        e.build()
+        for max_dist in (0.05, 0.3, 0.6, 0.97):
+            for order in (list(range(len(seqs))), list(range(len(seqs)))[::-1], rng.sample(range(len(seqs)), 25)):
+                reps, want = [], []
+                for g in order:
+                    found = any(osets[r].distance(osets[g]) <= max_dist for r in reps)
+                    want.append(0 if found else 1)
+                    if not found:
+                        reps.append(g)
+                assert e.greedy_reps(order, max_dist).tolist() == want, (k, max_dist)
+        assert 1 < sum(e.greedy_reps(list(range(len(seqs))), 0.3)) < len(seqs)
