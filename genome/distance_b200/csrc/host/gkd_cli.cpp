@@ -403,7 +403,46 @@ struct JsonCursor {
                 case 'n': out += '\n'; break;
                 case 't': out += '\t'; break;
                 case 'r': out += '\r'; break;
-                case 'u': p += 4; out += '?'; break;
+                case 'b': out += '\b'; break;
+                case 'f': out += '\f'; break;
+                case 'u': {  // \uXXXX (with surrogate pairs) -> UTF-8, the bytes a Java PrintWriter would emit
+                    auto hex4 = [&](size_t at, uint32_t &v) {
+                        if (at + 4 > s.size()) return false;
+                        v = 0;
+                        for (size_t i = 0; i < 4; i++) {
+                            const char h = s[at + i];
+                            v <<= 4;
+                            if (h >= '0' && h <= '9') v |= (uint32_t)(h - '0');
+                            else if (h >= 'a' && h <= 'f') v |= (uint32_t)(h - 'a' + 10);
+                            else if (h >= 'A' && h <= 'F') v |= (uint32_t)(h - 'A' + 10);
+                            else return false;
+                        }
+                        return true;
+                    };
+                    uint32_t cp = 0, lo = 0;
+                    if (!hex4(p, cp)) throw IOException("malformed GTO: bad \\u escape");
+                    p += 4;
+                    if (cp >= 0xD800 && cp < 0xDC00 && p + 6 <= s.size() && s[p] == '\\' && s[p + 1] == 'u' && hex4(p + 2, lo) &&
+                        lo >= 0xDC00 && lo < 0xE000) {
+                        cp = 0x10000 + ((cp - 0xD800) << 10) + (lo - 0xDC00);
+                        p += 6;
+                    }
+                    if (cp < 0x80) out += (char)cp;
+                    else if (cp < 0x800) {
+                        out += (char)(0xC0 | (cp >> 6));
+                        out += (char)(0x80 | (cp & 0x3F));
+                    } else if (cp < 0x10000) {
+                        out += (char)(0xE0 | (cp >> 12));
+                        out += (char)(0x80 | ((cp >> 6) & 0x3F));
+                        out += (char)(0x80 | (cp & 0x3F));
+                    } else {
+                        out += (char)(0xF0 | (cp >> 18));
+                        out += (char)(0x80 | ((cp >> 12) & 0x3F));
+                        out += (char)(0x80 | ((cp >> 6) & 0x3F));
+                        out += (char)(0x80 | (cp & 0x3F));
+                    }
+                    break;
+                }
                 default: out += e;
                 }
             } else out += s[p++];

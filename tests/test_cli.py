@@ -181,6 +181,12 @@ def test_distreps_validation(tmp_path):
     assert rc == 1 and "is required" in err
 
 
+def _name(gid):
+    """genome names with non-ASCII characters: json.dump writes them as \\uXXXX escapes (one of them a surrogate
+    pair), which the GTO reader must turn back into the UTF-8 bytes a Java PrintWriter would print"""
+    return "Genus species " + gid + (" str. \u00e9\u2013\U0001d11e" if gid.endswith(("1", "4")) else "")
+
+
 @pytest.mark.gpu
 def test_distreps_matches_reference_greedy(orc, tmp_path):
     """DistanceRepsProcessor.java:185-274: greedy representatives, closest-representative assignment,
@@ -195,7 +201,7 @@ def test_distreps_matches_reference_greedy(orc, tmp_path):
     src.mkdir()
     for gid, contigs in genomes.items():
         with open(src / (gid + ".gto"), "w") as f:
-            json.dump({"id": gid, "scientific_name": "Genus species " + gid,
+            json.dump({"id": gid, "scientific_name": _name(gid),
                        "contigs": [{"id": "c%d" % j, "dna": c} for j, c in enumerate(contigs)]}, f)
     order = sorted(genomes)  # the source lists genomes in file-name order
     k, max_dist = 12, 0.6
@@ -216,13 +222,13 @@ def test_distreps_matches_reference_greedy(orc, tmp_path):
                 if x < d:
                     rep, d = r, x
         counts[rep] = counts.get(rep, 0) + 1
-        want_list.append("\t".join([g, "Genus species " + g, rep, "Genus species " + rep, orc.java_double(d)]))
+        want_list.append("\t".join([g, _name(g), rep, _name(rep), orc.java_double(d)]))
     out_dir = tmp_path / "out"
     rc, out, err = run(["distReps", "-K", str(k), "--dist", str(max_dist), "-D", str(out_dir), str(src)])
     assert rc == 0, err
     prefix = "rep%.4f_K%d" % (max_dist, k)
-    assert (out_dir / (prefix + ".list.tbl")).read_text().rstrip("\n").split("\n") == want_list
-    stats = (out_dir / (prefix + ".stats.tbl")).read_text().rstrip("\n").split("\n")
+    assert (out_dir / (prefix + ".list.tbl")).read_text(encoding="utf-8").rstrip("\n").split("\n") == want_list
+    stats = (out_dir / (prefix + ".stats.tbl")).read_text(encoding="utf-8").rstrip("\n").split("\n")
     assert stats[0] == "rep_id\trep_name\tsize"
     got = {ln.split("\t")[0]: int(ln.split("\t")[2]) for ln in stats[1:]}
     assert got == counts and 1 < len(reps) < len(order)
@@ -233,4 +239,4 @@ def test_distreps_matches_reference_greedy(orc, tmp_path):
     rc, out, err = run(["distReps", "-K", str(k), "--dist", str(max_dist), "-D", str(out_dir), "--clear", str(src)])
     assert rc == 0, err
     assert sorted(p.name for p in out_dir.iterdir()) == [prefix + ".list.tbl", prefix + ".stats.tbl"]
-    assert (out_dir / (prefix + ".list.tbl")).read_text().rstrip("\n").split("\n") == want_list
+    assert (out_dir / (prefix + ".list.tbl")).read_text(encoding="utf-8").rstrip("\n").split("\n") == want_list
