@@ -120,62 +120,102 @@ __device__ __forceinline__ void decode_pair(const PairSource &src, uint64_t t, u
 template <typename LowT>
 __device__ __forceinline__ uint32_t merge_smem(uint32_t pa, uint32_t ea, uint32_t pb, uint32_t eb);
 
+#ifndef GKD_MERGE_UNROLL2
+#define GKD_MERGE_UNROLL2 1
+#endif
+#ifndef GKD_MERGE_ONE_LDS
+#define GKD_MERGE_ONE_LDS 0  // measured on B200 (300 genomes): 345 ms against 284 ms for the two-load step
+#endif
+
+#if GKD_MERGE_ONE_LDS
+// Experiment kept for the record: one shared-memory load per step (exactly one run advances; ties advance A and
+// are counted there), a single LDS with a selected address serving every lane.  It cuts the shared-memory
+// wavefronts (the kernel's co-limiter) by ~40 % but needs 10.5 instead of 8 instructions per step and puts two
+// selects on the load's dependency chain: slower overall (issue-bound), so the two-load step below is the default.
+#define GKD_MERGE_STEP(T, SZ)               \
+    "setp.le." T " ple, a, b;\n"           \
+    "setp.eq." T " peq, a, b;\n"           \
+    "@peq add.u32 %2, %2, 1;\n"            \
+    "@ple add.u32 %0, %0, " SZ ";\n"       \
+    "@!ple add.u32 %1, %1, " SZ ";\n"      \
+    "selp.u32 adr, %0, %1, ple;\n"         \
+    "ld.shared." T " v, [adr];\n"          \
+    "selp." T " a, v, a, ple;\n"           \
+    "selp." T " b, b, v, ple;\n"
+#define GKD_MERGE_REGS(T) ".reg .pred ple, peq, pgo;\n.reg ." T " a, b, v;\n.reg .u32 adr;\n"
+#define GKD_MERGE_COUNT2 ""
+#define GKD_MERGE_COUNT1 ""
+#else
+#define GKD_MERGE_STEP(T, SZ)               \
+    "setp.gt." T " pgt, a, b;\n"           \
+    "setp.lt." T " plt, a, b;\n"           \
+    "@!pgt add.u32 %0, %0, " SZ ";\n"      \
+    "@!plt add.u32 %1, %1, " SZ ";\n"      \
+    "@!pgt ld.shared." T " a, [%0];\n"     \
+    "@!plt ld.shared." T " b, [%1];\n"
+#define GKD_MERGE_REGS(T) ".reg .pred pgt, plt, pgo;\n.reg ." T " a, b;\n"
+#define GKD_MERGE_COUNT2 "add.u32 %2, %2, 2;\n"
+#define GKD_MERGE_COUNT1 "add.u32 %2, %2, 1;\n"
+#endif
+
+// With GKD_MERGE_UNROLL2 the loop runs two steps per trip while both runs hold at least two more keys (no exit
+// test between them), then finishes with the one-step loop.
+#define GKD_MERGE_BODY(T, SZ, TAG)                                                          \
+    "{\n"                                                                                   \
+    GKD_MERGE_REGS(T)                                                                       \
+    "ld.shared." T " a, [%0];\n"                                                            \
+    "ld.shared." T " b, [%1];\n"                                                            \
+    "setp.lt.u32 pgo, %0, %5;\n"                                                            \
+    "setp.lt.and.u32 pgo, %1, %6, pgo;\n"                                                   \
+    "@!pgo bra " TAG "_ONE_%=;\n"                                                           \
+    TAG "_TWO_%=:\n"                                                                        \
+    GKD_MERGE_STEP(T, SZ)                                                                   \
+    GKD_MERGE_STEP(T, SZ)                                                                   \
+    GKD_MERGE_COUNT2                                                                        \
+    "setp.lt.u32 pgo, %0, %5;\n"                                                            \
+    "setp.lt.and.u32 pgo, %1, %6, pgo;\n"                                                   \
+    "@pgo bra " TAG "_TWO_%=;\n"                                                            \
+    "setp.lt.u32 pgo, %0, %3;\n"                                                            \
+    "setp.lt.and.u32 pgo, %1, %4, pgo;\n"                                                   \
+    "@!pgo bra " TAG "_END_%=;\n"                                                           \
+    TAG "_ONE_%=:\n"                                                                        \
+    GKD_MERGE_STEP(T, SZ)                                                                   \
+    GKD_MERGE_COUNT1                                                                        \
+    "setp.lt.u32 pgo, %0, %3;\n"                                                            \
+    "setp.lt.and.u32 pgo, %1, %4, pgo;\n"                                                   \
+    "@pgo bra " TAG "_ONE_%=;\n"                                                            \
+    TAG "_END_%=:\n"                                                                        \
+    "}\n"
+
+// what merge_smem returns from its three in/out operands (pa, pb, and the step counter or the match counter)
+__device__ __forceinline__ uint32_t merge_result(uint32_t pa, uint32_t pb, uint32_t start, uint32_t counter, int shift) {
+#if GKD_MERGE_ONE_LDS
+    (void)pa, (void)pb, (void)start, (void)shift;
+    return counter;  // matches counted directly
+#else
+    return ((pa + pb - start) >> shift) - counter;  // every step advances one run, or both on a match
+#endif
+}
+
 template <>
 __device__ __forceinline__ uint32_t merge_smem<uint32_t>(uint32_t pa, uint32_t ea, uint32_t pb, uint32_t eb) {
     if (pa >= ea || pb >= eb) return 0;
     const uint32_t start = pa + pb;
-    uint32_t steps = 0;
-    asm volatile(
-        "{\n"
-        ".reg .pred pgt, plt, pgo;\n"
-        ".reg .u32 a, b;\n"
-        "ld.shared.u32 a, [%0];\n"
-        "ld.shared.u32 b, [%1];\n"
-        "MERGE32_%=:\n"
-        "setp.gt.u32 pgt, a, b;\n"
-        "setp.lt.u32 plt, a, b;\n"
-        "@!pgt add.u32 %0, %0, 4;\n"
-        "@!plt add.u32 %1, %1, 4;\n"
-        "add.u32 %2, %2, 1;\n"
-        "@!pgt ld.shared.u32 a, [%0];\n"
-        "@!plt ld.shared.u32 b, [%1];\n"
-        "setp.lt.u32 pgo, %0, %3;\n"
-        "setp.lt.and.u32 pgo, %1, %4, pgo;\n"
-        "@pgo bra MERGE32_%=;\n"
-        "}\n"
-        : "+r"(pa), "+r"(pb), "+r"(steps)
-        : "r"(ea), "r"(eb)
-        : "memory");
-    return ((pa + pb - start) >> 2) - steps;
+    uint32_t counter = 0;
+    // two unchecked steps need two keys left in each run: pa < ea - 4 and pb < eb - 4 (the runs are not empty here)
+    const uint32_t ea2 = GKD_MERGE_UNROLL2 ? ea - 4u : 0u, eb2 = GKD_MERGE_UNROLL2 ? eb - 4u : 0u;
+    asm volatile(GKD_MERGE_BODY("u32", "4", "M32") : "+r"(pa), "+r"(pb), "+r"(counter) : "r"(ea), "r"(eb), "r"(ea2), "r"(eb2) : "memory");
+    return merge_result(pa, pb, start, counter, 2);
 }
 
 template <>
 __device__ __forceinline__ uint32_t merge_smem<uint64_t>(uint32_t pa, uint32_t ea, uint32_t pb, uint32_t eb) {
     if (pa >= ea || pb >= eb) return 0;
     const uint32_t start = pa + pb;
-    uint32_t steps = 0;
-    asm volatile(
-        "{\n"
-        ".reg .pred pgt, plt, pgo;\n"
-        ".reg .u64 a, b;\n"
-        "ld.shared.u64 a, [%0];\n"
-        "ld.shared.u64 b, [%1];\n"
-        "MERGE64_%=:\n"
-        "setp.gt.u64 pgt, a, b;\n"
-        "setp.lt.u64 plt, a, b;\n"
-        "@!pgt add.u32 %0, %0, 8;\n"
-        "@!plt add.u32 %1, %1, 8;\n"
-        "add.u32 %2, %2, 1;\n"
-        "@!pgt ld.shared.u64 a, [%0];\n"
-        "@!plt ld.shared.u64 b, [%1];\n"
-        "setp.lt.u32 pgo, %0, %3;\n"
-        "setp.lt.and.u32 pgo, %1, %4, pgo;\n"
-        "@pgo bra MERGE64_%=;\n"
-        "}\n"
-        : "+r"(pa), "+r"(pb), "+r"(steps)
-        : "r"(ea), "r"(eb)
-        : "memory");
-    return ((pa + pb - start) >> 3) - steps;
+    uint32_t counter = 0;
+    const uint32_t ea2 = GKD_MERGE_UNROLL2 ? ea - 8u : 0u, eb2 = GKD_MERGE_UNROLL2 ? eb - 8u : 0u;
+    asm volatile(GKD_MERGE_BODY("u64", "8", "M64") : "+r"(pa), "+r"(pb), "+r"(counter) : "r"(ea), "r"(eb), "r"(ea2), "r"(eb2) : "memory");
+    return merge_result(pa, pb, start, counter, 3);
 }
 
 template <typename LowT>
