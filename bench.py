@@ -411,7 +411,8 @@ def main():
         except Exception:
             traffic = None
     kname = {3: "k_intersect_bucket<uint32_t> (bucket merge, 32-bit low words)",
-             4: "k_intersect_bucket<uint64_t> (bucket merge, 64-bit keys)"}
+             4: "k_intersect_bucket<uint64_t> (bucket merge, 64-bit keys)",
+             5: "k_join (block join: 32 row sets per shared-memory hash table, columns streamed once per row block)"}
     roofline = {"kernel": kname.get(int(mets[-1].get("intersect_kernel", 0)), "k_intersect_bucket"), "bound": "hbm",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "traffic_source": traffic_src, "peak_source": peak_src,

@@ -114,6 +114,8 @@ struct gkd_ctx {
     DevBuf sk_cand, sk_misc, sk_sig, sk_len, sk_out;
     DevBuf msd_genomes, msd_bins32, msd_bins64, msd_gstat;
     DevBuf gr_reps, gr_flags;
+    DevBuf join_rows, join_err;
+    int isect_algo = 0;  // GKD_ISECT_ALGO: 0 = choose per call, 1 = bucket merge only, 2 = block join whenever it applies
     bool use_msd = true;  // GKD_SORT_ALGO=lsd pins the LSD path
     bool sets_dirty = true;
 
@@ -825,6 +827,90 @@ void host_pair_ids(const HostPairs &hp, uint64_t t, uint32_t &a, uint32_t &b) {
     else a = hp.a[t], b = hp.b[t];
 }
 
+// Block-join planning (join.cu).  Decides whether the chunk [first, first+count) of an UPPER call, or a RECT
+// call, is served by the block join and lays out its row blocks: rows are grouped by the number of key ranges
+// their size calls for (so that 32 rows fill ~30 % of the table in every range), largest class first, a class
+// padded to whole blocks.  Returns false when the merge kernel should run.
+bool plan_join(gkd_ctx *c, const HostPairs &hp, uint64_t first, uint64_t count, JoinPlan &plan, std::vector<uint32_t> &rows,
+               bool &swapped) {
+    swapped = false;
+    if (c->isect_algo == 1 || c->low_bits != 32 || count == 0) return false;
+    if (hp.mode != PAIRS_UPPER && hp.mode != PAIRS_RECT) return false;
+    const bool forced = c->isect_algo == 2;
+    const uint32_t lt_min = (uint32_t)std::max(1, c->key_bits - 31), lt_max = (uint32_t)c->key_bits - 1u;
+    if (lt_min > lt_max) return false;
+    const uint32_t slots = join_table_slots();
+    uint32_t fill_pct = 30;
+    if (const char *e = getenv("GKD_JOIN_FILL")) fill_pct = (uint32_t)std::min(45, std::max(5, atoi(e)));
+    const uint64_t fill = std::max<uint64_t>(32, (uint64_t)slots * fill_pct / 100);
+
+    // candidate rows and the columns they meet
+    std::vector<uint32_t> cand;  // UPPER: set ids; RECT: positions in the row-side id list
+    const uint32_t *row_ids = nullptr;
+    uint32_t n_cols = 0;
+    if (hp.mode == PAIRS_UPPER) {
+        uint32_t i0, j0, i1, j1;
+        upper_pair(first, hp.n, i0, j0);
+        upper_pair(first + count - 1, hp.n, i1, j1);
+        for (uint32_t i = i0; i <= i1; i++) cand.push_back(i);
+        n_cols = hp.n;
+        // a thin slice of the triangle would stream every column for a few pairs
+        if (!forced && count < (uint64_t)cand.size() * (hp.n - i0) / 4) return false;
+    } else {
+        // the table side needs whole blocks of rows, the streamed side many columns
+        swapped = hp.na < 32 && hp.nb >= 32;
+        const uint32_t nr = swapped ? hp.nb : hp.na;
+        row_ids = swapped ? hp.b : hp.a;
+        n_cols = swapped ? hp.na : hp.nb;
+        for (uint32_t i = 0; i < nr; i++) cand.push_back(i);
+    }
+    auto size_at = [&](uint32_t e) -> uint64_t { return c->genomes[row_ids ? row_ids[e] : e].desc.main.n; };
+    uint64_t n_max = 0;
+    std::vector<std::pair<uint32_t, uint32_t>> byl;  // (level, entry)
+    for (uint32_t e : cand) {
+        const uint64_t n = size_at(e);
+        if (n == 0) continue;  // nothing can match: the counts stay 0
+        n_max = std::max(n_max, n);
+        uint32_t L = ceil_log2_u32((uint32_t)std::min<uint64_t>(0xFFFFFFFFull, (32ull * n + fill - 1) / fill));
+        L = std::min(std::max(L, lt_min), lt_max);
+        byl.push_back({L, e});
+    }
+    if (byl.empty()) return false;
+    if (!forced) {
+        // enough rows to share a probe, enough columns to pay for building the tables, and sets large enough
+        // that the tables of the coarsest usable range are not almost empty
+        if (byl.size() < 16 || n_cols < 64) return false;
+        if (32ull * n_max < (fill << lt_min) / 4) return false;
+    }
+    std::stable_sort(byl.begin(), byl.end(), [](const auto &x, const auto &y) { return x.first > y.first; });
+    plan = JoinPlan{};
+    plan.mode = hp.mode;
+    plan.key_bits = c->key_bits;
+    plan.n_cols = n_cols;
+    plan.first = first;
+    plan.count = count;
+    plan.stride_r = swapped ? 1ull : (unsigned long long)hp.nb;
+    plan.stride_c = swapped ? (unsigned long long)hp.nb : 1ull;
+    rows.clear();
+    unsigned long long tasks = 0;
+    for (size_t i = 0; i < byl.size();) {
+        size_t j = i;
+        while (j < byl.size() && byl[j].first == byl[i].first) j++;
+        if (plan.n_classes >= (uint32_t)JOIN_MAX_CLASSES) return false;
+        JoinClass &k = plan.cls[plan.n_classes++];
+        k.level = byl[i].first;
+        k.blk_first = (uint32_t)(rows.size() / 32);
+        for (size_t t = i; t < j; t++) rows.push_back(byl[t].second);
+        while (rows.size() % 32) rows.push_back(0xFFFFFFFFu);
+        k.n_blocks = (uint32_t)(rows.size() / 32) - k.blk_first;
+        k.task_first = tasks;
+        tasks += (unsigned long long)k.n_blocks << k.level;
+        i = j;
+    }
+    plan.n_tasks = tasks;
+    return true;
+}
+
 int run_pairs(gkd_ctx *c, const HostPairs &hp, const gkd_outputs &out) {
     int rc = upload_sets(c);
     if (rc) return rc;
@@ -891,7 +977,6 @@ int run_pairs(gkd_ctx *c, const HostPairs &hp, const gkd_outputs &out) {
     c->m.total_intersect_bytes += (uint64_t)sum_bytes;
     c->m.total_pairs += hp.count;
     if (hp.count == 0) return GKD_OK;
-    c->m.intersect_kernel = c->low_bits == 32 ? 3u : 4u;
 
     // work split: a pair is walked in 32-bucket groups at the level of its larger set; an item is a run
     // of groups of one pair.  Few pairs -> small items so every warp has work; many pairs -> eight items
@@ -933,9 +1018,14 @@ int run_pairs(gkd_ctx *c, const HostPairs &hp, const gkd_outputs &out) {
     }
     if ((rc = ensure(c, c->work_counter, 8))) return rc;
 
-    for (uint64_t done = 0; done < hp.count; done += PAIR_CHUNK) {
+    bool join_banned = false;  // set when a join table overflowed: the chunk is redone by the merge kernel
+    JoinPlan jplan{};
+    std::vector<uint32_t> jrows;
+    for (uint64_t done = 0; done < hp.count;) {
         const uint64_t cnt = std::min<uint64_t>(PAIR_CHUNK, hp.count - done);
         src.count = cnt;
+        bool jswapped = false;
+        const bool use_join = !join_banned && plan_join(c, hp, hp.mode == PAIRS_UPPER ? hp.first + done : 0, cnt, jplan, jrows, jswapped);
         if (hp.mode == PAIRS_UPPER) {
             src.first = hp.first + done;
             src.a = src.b = nullptr;
@@ -963,12 +1053,35 @@ int run_pairs(gkd_ctx *c, const HostPairs &hp, const gkd_outputs &out) {
         if (out.contain_a && (rc = ensure(c, c->d_ca, cnt * 8))) return rc;
         if (out.contain_b && (rc = ensure(c, c->d_cb, cnt * 8))) return rc;
 
+        if (use_join) {
+            if ((rc = ensure(c, c->join_rows, jrows.size() * 4))) return rc;
+            if ((rc = ensure(c, c->join_err, 4))) return rc;
+            CK(cudaMemcpyAsync(c->join_rows.p, jrows.data(), jrows.size() * 4, cudaMemcpyHostToDevice, c->stream));
+            CK(cudaMemsetAsync(c->join_err.p, 0, 4, c->stream));
+            jplan.rows = (const uint32_t *)c->join_rows.p;
+            if (hp.mode == PAIRS_RECT) {
+                jplan.row_ids = (const uint32_t *)(jswapped ? c->ids_b.p : c->ids_a.p);
+                jplan.col_ids = (const uint32_t *)(jswapped ? c->ids_a.p : c->ids_b.p);
+            }
+        }
         CK(cudaEventRecord(c->ev[4], c->stream));
-        nvtxRangePushA("gkd kernel 4: bucket-merge intersect");
-        CK(launch_intersect((const SetDesc *)c->d_sets.p, src, 0, plan, (uint32_t *)c->counts.p,
-                            (unsigned long long *)c->work_counter.p, c->n_sms, c->stream));
+        if (use_join) {
+            nvtxRangePushA("gkd kernel 4: block join");
+            CK(launch_join((const SetDesc *)c->d_sets.p, jplan, (uint32_t *)c->counts.p,
+                           (unsigned long long *)c->work_counter.p, (uint32_t *)c->join_err.p, c->n_sms, c->stream));
+        } else {
+            nvtxRangePushA("gkd kernel 4: bucket-merge intersect");
+            CK(launch_intersect((const SetDesc *)c->d_sets.p, src, 0, plan, (uint32_t *)c->counts.p,
+                                (unsigned long long *)c->work_counter.p, c->n_sms, c->stream));
+        }
         nvtxRangePop();
         CK(cudaEventRecord(c->ev[5], c->stream));
+        c->m.intersect_kernel = use_join ? 5u : (c->low_bits == 32 ? 3u : 4u);
+        uint32_t join_err = 0;
+        if (use_join) {
+            // a table that would overflow flags the launch; the chunk is then redone by the merge kernel
+            CK(cudaMemcpyAsync(&join_err, c->join_err.p, 4, cudaMemcpyDeviceToHost, c->stream));
+        }
         c->m.launches++;
         c->m.intersect_launches++;
         if (need_pal && max_pal) {
@@ -1004,6 +1117,10 @@ int run_pairs(gkd_ctx *c, const HostPairs &hp, const gkd_outputs &out) {
             d2h += cnt * 8;
         }
         CK(cudaStreamSynchronize(c->stream));
+        if (join_err) {
+            join_banned = true;
+            continue;
+        }
         c->m.d2h_bytes += d2h;
         const double ims = elapsed(c->ev[4], c->ev[5]);
         c->m.intersect_ms += ims;
@@ -1025,6 +1142,7 @@ int run_pairs(gkd_ctx *c, const HostPairs &hp, const gkd_outputs &out) {
                 if (out.contain_b) out.contain_b[done + t] = sb ? (double)I / (double)sb : 0.0;
             }
         }
+        done += PAIR_CHUNK;
     }
     return GKD_OK;
 }
@@ -1106,10 +1224,12 @@ int gkd_create(gkd_ctx **out, const gkd_config *cfg) {
     for (auto &ev : c->ev) CK_CREATE(cudaEventCreate(&ev));
     // function attributes are per device: every context sets them for its own device
     CK_CREATE(intersect_configure());
+    CK_CREATE(join_configure());
     CK_CREATE(sort_configure());
     CK_CREATE(sketch_configure());
     CK_CREATE(msd_configure());
     if (const char *a = getenv("GKD_SORT_ALGO")) c->use_msd = !(a[0] == 'l' || a[0] == 'L');
+    if (const char *a = getenv("GKD_ISECT_ALGO")) c->isect_algo = (a[0] == 'm' || a[0] == 'M') ? 1 : (a[0] == 'j' || a[0] == 'J') ? 2 : 0;
 #undef CK_CREATE
     *out = c;
     return GKD_OK;
@@ -1181,7 +1301,7 @@ int gkd_destroy(gkd_ctx *c) {
                       &c->set_build, &c->d_sets, &c->counts, &c->pal_counts, &c->d_inter, &c->d_dist, &c->d_ca,
                       &c->d_cb, &c->ids_a, &c->ids_b, &c->work_counter, &c->sk_cand, &c->sk_misc, &c->sk_sig,
                       &c->sk_len, &c->sk_out, &c->msd_genomes, &c->msd_bins32, &c->msd_bins64, &c->msd_gstat,
-                      &c->gr_reps, &c->gr_flags};
+                      &c->gr_reps, &c->gr_flags, &c->join_rows, &c->join_err};
     for (DevBuf *b : bufs)
         if (b->p) cudaFreeAsync(b->p, c->stream);
     cudaStreamSynchronize(c->stream);

@@ -1,0 +1,310 @@
+// join.cu -- kernel 4, block-join form: 32 row sets against every column set at once.
+//
+// Reference semantics restated (same as intersect.cu): SequenceKmers.similarity = number of members of one
+// HashSet<String> found in the other, for every pair the caller enumerates -- the strict upper triangle of
+// FastaDistanceProcessor.java:174-194 or the query x reference rectangle of GenomeProcessor.java:129-147.
+// The reference probes one hash set with the members of the other, pair by pair.  The bucket-merge kernel
+// (intersect.cu) streams both sets of every pair; for a pair MATRIX that repeats the same work row after row:
+// a column key is compared with every row separately.  This kernel keeps the reference's probe formulation but
+// shares the probe between 32 rows:
+//
+//   * the key space is cut into 2^L equal ranges (L per class of row sizes, chosen so that the keys 32 rows
+//     hold in one range fill ~30 % of the table).  Sets are stored in mixed-key order with bucket offset
+//     tables (gkd_internal.cuh), so the keys any set holds in a range are one contiguous run of its low words;
+//   * a task = (block of 32 rows, range).  The CTA builds ONE open-addressing table in shared memory:
+//     key (32-bit low word; the range pins the other bits) -> 32-bit mask of the rows that hold it
+//     (find-or-insert with atomicCAS on the key word, atomicOr on the mask word: lock-free, no ordering
+//     between rows needed);
+//   * then every column set's run of the same range is streamed once from L2/HBM (coalesced, 4 keys per lane
+//     in flight) and probed; a hit returns the row mask.  Misses -- nearly every probe of an unrelated
+//     genome -- cost one shared-memory load for 32 pairs at once;
+//   * hits are tallied per row with ballots (lane r keeps the count of row r) and flushed with one
+//     atomicAdd per (row, column, range) that saw a match.
+//
+// Per pair and column key this is 1/32 of a probe instead of a two-pointer merge step, and every set is read
+// once per ROW BLOCK instead of once per row; tasks are enumerated range-major so the column runs of one range
+// are served from L2 to all row blocks.  Counts are exact (a key's identity inside a range is its low word).
+// Used for 32-bit low words (DNA/RNA K <= 21, protein K <= 5) when a call has enough rows and columns;
+// everything else (lists, greedy pass, 64-bit keys, tiny sets, palindrome sub-sets) stays on the merge kernel.
+#include <cstdlib>
+
+#include "gkd_internal.cuh"
+
+namespace gkd {
+
+namespace {
+
+constexpr uint32_t JOIN_INVALID = 0xFFFFFFFFu;
+
+// where set S keeps the keys of range rho (level L): run [lo, hi) of its low words, plus a value filter
+// when the set's own table is coarser than the range (fm == 0: every key of the run is in the range)
+struct RangeRun {
+    const uint32_t *lows;
+    uint32_t lo, hi, fm, fv;
+};
+
+__device__ __forceinline__ RangeRun range_run(const SubSet &S, uint32_t L, uint32_t rho) {
+    RangeRun r;
+    r.lows = (const uint32_t *)S.lows;
+    r.lo = r.hi = 0;
+    r.fm = r.fv = 0;
+    if (S.n == 0) return r;
+    if (S.level >= L) {
+        const uint32_t sh = S.level - L;
+        r.lo = __ldg(S.offs + ((size_t)rho << sh));
+        r.hi = __ldg(S.offs + ((size_t)(rho + 1) << sh));
+    } else {  // coarser table: take the enclosing bucket and keep the keys whose next bits select this range
+        const uint32_t d = L - S.level;
+        const uint32_t c = rho >> d;
+        r.lo = __ldg(S.offs + c);
+        r.hi = __ldg(S.offs + c + 1);
+        r.fm = (1u << d) - 1u;
+        r.fv = rho & r.fm;
+    }
+    return r;
+}
+
+template <int SLOTS_LOG2>
+__device__ __forceinline__ uint32_t join_hash(uint32_t k) {
+    return (k * 0x9E3779B1u) >> (32 - SLOTS_LOG2);
+}
+
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {  // shared-window address: no generic-pointer set-up per load
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+
+constexpr int KPT = 6;  // column keys per lane per trip: a run of ~150 keys (30 % fill / 32 rows) is one trip
+
+}  // namespace
+
+template <int SLOTS_LOG2, int THREADS, int CTAS>
+__global__ void __launch_bounds__(THREADS, CTAS)
+    k_join(const SetDesc *__restrict__ sets, JoinPlan plan, uint32_t *__restrict__ counts,
+           unsigned long long *__restrict__ work_counter, uint32_t *__restrict__ err) {
+    constexpr uint32_t SLOTS = 1u << SLOTS_LOG2, SMASK = SLOTS - 1u;
+    constexpr uint32_t MAXFILL = SLOTS / 2u + SLOTS / 8u;
+    constexpr int NW = THREADS / 32;
+    extern __shared__ __align__(16) uint32_t sm_tab[];
+    uint32_t *keys = sm_tab, *masks = sm_tab + SLOTS;
+    __shared__ unsigned long long s_task;
+    __shared__ uint32_t s_rowid[32], s_rowpos[32];
+    __shared__ uint32_t s_fill, s_cbeg;
+    __shared__ RangeRun s_run[32];
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    const uint32_t FULL = 0xffffffffu;
+
+    for (;;) {
+        if (tid == 0) s_task = atomicAdd(work_counter, 1ull);
+        __syncthreads();  // also: every warp is done probing the previous table
+        const unsigned long long task = s_task;
+        if (task >= plan.n_tasks) return;
+        // task -> (class, range, row block); range-major inside a class
+        uint32_t ci = 0;
+        while (ci + 1 < plan.n_classes && task >= plan.cls[ci + 1].task_first) ci++;
+        const uint32_t L = plan.cls[ci].level;
+        const unsigned long long local = task - plan.cls[ci].task_first;
+        const uint32_t rho = (uint32_t)(local / plan.cls[ci].n_blocks);
+        const uint32_t blk = plan.cls[ci].blk_first + (uint32_t)(local % plan.cls[ci].n_blocks);
+        const uint32_t fs = (uint32_t)plan.key_bits - L;  // 1..31: low-word bits below the range index
+        // no key of the range has this low word: bit 31 lies inside the range index and is flipped
+        const uint32_t EMPTY = ((uint32_t)((unsigned long long)rho << fs)) ^ 0x80000000u;
+
+        {  // clear the table
+            uint4 *k4 = (uint4 *)keys, *m4 = (uint4 *)masks;
+            const uint4 e4 = make_uint4(EMPTY, EMPTY, EMPTY, EMPTY), z4 = make_uint4(0, 0, 0, 0);
+            for (uint32_t i = tid; i < SLOTS / 4; i += THREADS) {
+                k4[i] = e4;
+                m4[i] = z4;
+            }
+        }
+        if (warp == 0) {
+            // lane r looks up row r of the block and its run of this range; the runs' total is checked
+            // before anything is inserted, so the table can never fill up
+            const uint32_t pos = plan.rows[(size_t)blk * 32u + lane];
+            uint32_t id = JOIN_INVALID;
+            if (pos != JOIN_INVALID) id = plan.row_ids ? plan.row_ids[pos] : pos;
+            s_rowpos[lane] = pos;
+            s_rowid[lane] = id;
+            RangeRun rr{};
+            if (id != JOIN_INVALID) rr = range_run(sets[id].main, L, rho);
+            s_run[lane] = rr;
+            const uint32_t total = __reduce_add_sync(FULL, rr.hi - rr.lo);
+            const uint32_t mn = __reduce_min_sync(FULL, id);
+            if (lane == 0) {
+                s_fill = total;
+                s_cbeg = plan.mode == PAIRS_UPPER ? mn + 1u : 0u;  // columns right of the block's first row
+            }
+        }
+        __syncthreads();
+
+        // ---- build: the rows' runs of this range go into the table -------------------------------------
+        if (s_fill > MAXFILL) {
+            if (tid == 0) atomicExch(err, 1u);  // the host redoes the call with the merge kernel
+            continue;
+        }
+        for (uint32_t r = warp; r < 32u; r += NW) {
+            const RangeRun rr = s_run[r];
+            const uint32_t bit = 1u << r;
+            for (uint32_t i = rr.lo + lane; i < rr.hi; i += 32u) {
+                const uint32_t k = __ldg(rr.lows + i);
+                if (((k >> fs) & rr.fm) != rr.fv) continue;
+                uint32_t s = join_hash<SLOTS_LOG2>(k);
+                for (;;) {
+                    const uint32_t old = atomicCAS(&keys[s], EMPTY, k);
+                    if (old == EMPTY || old == k) {
+                        atomicOr(&masks[s], bit);
+                        break;
+                    }
+                    s = (s + 1u) & SMASK;
+                }
+            }
+        }
+        __syncthreads();
+
+        // ---- probe: stream every column's run of the range ---------------------------------------------
+        // Warp w takes the columns cbeg + w, cbeg + w + NW, ... (related genomes have neighbouring ids, so the
+        // expensive columns spread over all warps); 32 of them are prepared at a time, one per lane, and the
+        // keys of the next column are requested before the current one is probed.  A column's run of a range
+        // (~150 keys at the default fill) fits one trip of KPT keys per lane.
+        const uint32_t cend = plan.n_cols;
+        const uint32_t my_rowid = s_rowid[lane], my_rowpos = s_rowpos[lane];
+        const uint32_t kbase = (uint32_t)__cvta_generic_to_shared(keys);
+        constexpr uint32_t M4 = SMASK << 2, MASKS_OFF = SLOTS * 4u;
+        for (uint32_t g0 = s_cbeg + warp; g0 < cend; g0 += 32u * NW) {
+            const uint32_t c_mine = g0 + lane * NW;
+            uint32_t col_id = 0;
+            RangeRun cr{};
+            if (c_mine < cend) {
+                col_id = plan.col_ids ? plan.col_ids[c_mine] : c_mine;
+                cr = range_run(sets[col_id].main, L, rho);
+            }
+            uint32_t nb = (cend - g0 + NW - 1u) / NW;
+            if (nb > 32u) nb = 32u;
+            uint32_t nk[KPT], nlo, nhi;
+            const uint32_t *nlows;
+            auto fetch = [&](uint32_t j) {
+                nlo = __shfl_sync(FULL, cr.lo, j);
+                nhi = __shfl_sync(FULL, cr.hi, j);
+                nlows = (const uint32_t *)__shfl_sync(FULL, (unsigned long long)cr.lows, j);
+#pragma unroll
+                for (int q = 0; q < KPT; q++) {
+                    const uint32_t i = nlo + q * 32u + lane;
+                    nk[q] = i < nhi ? __ldg(nlows + i) : 0u;
+                }
+            };
+            fetch(0);
+            for (uint32_t j = 0; j < nb; j++) {
+                const uint32_t lo = nlo, hi = nhi;
+                const uint32_t *lows = nlows;
+                uint32_t k[KPT];
+#pragma unroll
+                for (int q = 0; q < KPT; q++) k[q] = nk[q];
+                if (j + 1 < nb) fetch(j + 1);
+                if (lo >= hi) continue;
+                const uint32_t fm = __shfl_sync(FULL, cr.fm, j), fv = __shfl_sync(FULL, cr.fv, j);
+                const uint32_t cid = __shfl_sync(FULL, col_id, j);
+                // rows that form a requested pair with this column (upper triangle: row id < column id)
+                const uint32_t rowmask = plan.mode == PAIRS_UPPER ? __ballot_sync(FULL, my_rowid < cid) : FULL;
+                // matches: acc[g] holds four 8-bit counters, byte b = row g + 8b, of THIS lane's keys
+                uint32_t acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+                uint32_t pending = 0;  // trips added to acc since the last flush (warp-uniform)
+                uint32_t cnt = 0;      // lane r: matches of row r with this column in this range
+                auto flush = [&]() {
+#pragma unroll
+                    for (int g = 0; g < 8; g++) {
+                        const uint32_t even = __reduce_add_sync(FULL, acc[g] & 0x00FF00FFu);         // rows g, g+16
+                        const uint32_t odd = __reduce_add_sync(FULL, (acc[g] >> 8) & 0x00FF00FFu);   // rows g+8, g+24
+                        const uint32_t v = (lane & 8u) ? odd : even;
+                        if ((lane & 7u) == (uint32_t)g) cnt += (lane & 16u) ? (v >> 16) : (v & 0xFFFFu);
+                        acc[g] = 0;
+                    }
+                    pending = 0;
+                };
+                for (uint32_t base = lo; base < hi; base += 32u * KPT) {
+                    uint32_t m[KPT], anym = 0;
+#pragma unroll
+                    for (int q = 0; q < KPT; q++) {
+                        const uint32_t i = base + q * 32u + lane;
+                        if (base != lo) k[q] = i < hi ? __ldg(lows + i) : 0u;
+                        const bool ok = i < hi && ((k[q] >> fs) & fm) == fv;
+                        uint32_t a = kbase + (((k[q] * 0x9E3779B1u) >> (30 - SLOTS_LOG2)) & M4);
+                        uint32_t e = ok ? lds_u32(a) : EMPTY;
+                        while (e != k[q] && e != EMPTY) {
+                            a = kbase + ((a - kbase + 4u) & M4);
+                            e = lds_u32(a);
+                        }
+                        m[q] = (ok && e == k[q]) ? (lds_u32(a + MASKS_OFF) & rowmask) : 0u;
+                        anym |= m[q];
+                    }
+                    if (__any_sync(FULL, anym != 0u)) {
+#pragma unroll
+                        for (int q = 0; q < KPT; q++) {
+#pragma unroll
+                            for (int g = 0; g < 8; g++) acc[g] += (m[q] >> g) & 0x01010101u;
+                        }
+                        if (++pending == 255u / KPT) flush();  // before a byte counter can overflow
+                    }
+                }
+                if (pending) flush();
+                if (cnt) {
+                    unsigned long long t;
+                    bool valid = true;
+                    if (plan.mode == PAIRS_UPPER) {
+                        const unsigned long long i = my_rowid, n = plan.n_cols;
+                        t = i * (2ull * n - i - 1ull) / 2ull + ((unsigned long long)cid - i - 1ull) - plan.first;
+                        valid = t < plan.count;  // pairs before `first` wrap around to huge values
+                    } else {
+                        t = (unsigned long long)my_rowpos * plan.stride_r + (unsigned long long)(g0 + j * NW) * plan.stride_c;
+                    }
+                    if (valid) atomicAdd(&counts[t], cnt);
+                }
+            }
+        }
+    }
+}
+
+// Table geometries: <log2 slots, threads per CTA, CTAs per SM>; keys + masks = 8 bytes per slot
+#define GKD_FOR_EACH_JCFG(X) X(0, 14, 1024, 1) X(1, 13, 320, 3) X(2, 13, 256, 3) X(3, 14, 512, 1) X(4, 12, 160, 6) X(5, 12, 128, 6) X(6, 13, 512, 2) X(7, 12, 256, 4)
+constexpr int N_JCFG = 8;
+constexpr int DEFAULT_JCFG = 0;
+static const int g_jcfg_slots_log2[N_JCFG] = {14, 13, 13, 14, 12, 12, 13, 12};
+
+static int env_jcfg() {
+    const char *e = getenv("GKD_JOIN_CFG");
+    int c = e ? atoi(e) : DEFAULT_JCFG;
+    return (c < 0 || c >= N_JCFG) ? DEFAULT_JCFG : c;
+}
+
+uint32_t join_table_slots() { return 1u << g_jcfg_slots_log2[env_jcfg()]; }
+
+cudaError_t join_configure() {
+    cudaError_t e;
+#define X(i, SL, T, C)                                                                                              \
+    if ((e = cudaFuncSetAttribute(k_join<SL, T, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (8 << SL))) != cudaSuccess) \
+        return e;
+    GKD_FOR_EACH_JCFG(X)
+#undef X
+    return cudaSuccess;
+}
+
+cudaError_t launch_join(const SetDesc *sets, const JoinPlan &plan, uint32_t *counts, unsigned long long *work_counter,
+                        uint32_t *err, int n_sms, cudaStream_t s) {
+    if (plan.n_tasks == 0) return cudaSuccess;
+    cudaError_t e = cudaMemsetAsync(work_counter, 0, sizeof(unsigned long long), s);
+    if (e != cudaSuccess) return e;
+    const int c = env_jcfg();
+#define X(i, SL, T, C)                                                                           \
+    if (c == i) {                                                                                \
+        unsigned long long grid = (unsigned long long)n_sms * C;                                 \
+        if (grid > plan.n_tasks) grid = plan.n_tasks;                                            \
+        k_join<SL, T, C><<<(unsigned)grid, T, (8 << SL), s>>>(sets, plan, counts, work_counter, err); \
+        return cudaGetLastError();                                                               \
+    }
+    GKD_FOR_EACH_JCFG(X)
+#undef X
+    return cudaErrorInvalidValue;
+}
+
+}  // namespace gkd
