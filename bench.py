@@ -400,10 +400,12 @@ def main():
         isect_ms = float(t[0])
     achieved = isect_bytes / (isect_ms * 1e-3) / 1e9 if isect_ms > 0 else 0.0
     traffic, traffic_src, stored = None, None, None
+    kernel_id = int(mets[-1].get("intersect_kernel", 0))
+    joined = kernel_id == 5
     tpath = os.path.join(ROOT, "profiles", "intersect_traffic.json")
     if os.path.exists(tpath):
         try:
-            tj = json.load(open(tpath))
+            tj = json.load(open(tpath))["join" if joined else "merge"]
             traffic = tj["dram_bytes_per_algorithmic_byte"] * isect_bytes
             traffic_src = ("ESTIMATED, not measured in this run: ncu dram__bytes_read+write per algorithmic byte of the "
                            f"profiled launch ({tj.get('source', 'profiles/')}) x this run's algorithmic bytes")
@@ -412,16 +414,26 @@ def main():
             traffic = None
     kname = {3: "k_intersect_bucket<uint32_t> (bucket merge, 32-bit low words)",
              4: "k_intersect_bucket<uint64_t> (bucket merge, 64-bit keys)",
-             5: "k_join (block join: 32 row sets per shared-memory hash table, columns streamed once per row block)"}
-    roofline = {"kernel": kname.get(int(mets[-1].get("intersect_kernel", 0)), "k_intersect_bucket"), "bound": "hbm",
+             5: "k_join (block join: 64 row sets share one shared-memory hash table per key range; every column set "
+                "is probed once per row block)"}
+    if joined:
+        note = ("achieved = 8*(|A|+|B|) bytes per pair (SURVEY 8d definition: two sorted uint64 sets streamed per pair) / "
+                "CUDA-event time of kernel 4.  The block join does NOT stream both sets per pair: one probe of a column key "
+                "serves 64 rows, every column set is read once per block of 64 rows (from L2: the tasks run range-major) "
+                "and once per step from HBM, so the algorithmic figure is far above the HBM peak and says how much "
+                "pair-streaming work was avoided, not how busy HBM is.  moved_frac = bytes actually moved L2->SM / time / "
+                "peak (estimated from the committed ncu ratio); the kernel's limiter is SM instruction issue and "
+                "shared-memory probe latency (62 % issue slots busy in profiles/r2j_join_ncu_full.txt)")
+    else:
+        note = ("achieved = 8*(|A|+|B|) bytes per pair (SURVEY 8d definition: sorted uint64 sets) / CUDA-event time "
+                "of kernel 4.  The kernel reads the sets in a compressed layout (32-bit low words + bucket table, "
+                "~4.25 stored bytes per key) and the row sets are served from L2, so the algorithmic figure can "
+                "exceed the HBM peak; stored_frac is the same fraction on the bytes actually stored")
+    roofline = {"kernel": kname.get(kernel_id, "k_intersect_bucket"), "bound": "hbm",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "traffic_source": traffic_src, "peak_source": peak_src,
-                "algorithmic_bytes_per_step": isect_bytes, "ms_per_step": isect_ms,
-                "note": "achieved = 8*(|A|+|B|) bytes per pair (SURVEY 8d definition: sorted uint64 sets) / CUDA-event time "
-                        "of kernel 4.  The kernel reads the sets in a compressed layout (32-bit low words + bucket table, "
-                        "~4.25 stored bytes per key) and the row sets are served from L2, so the algorithmic figure can "
-                        "exceed the HBM peak; stored_frac is the same fraction on the bytes actually stored",
-                "stored_frac": (achieved / peak) * stored if stored else None}
+                "algorithmic_bytes_per_step": isect_bytes, "ms_per_step": isect_ms, "note": note,
+                ("moved_frac" if joined else "stored_frac"): (achieved / peak) * stored if stored else None}
     build_ms = sum(m["encode_ms"] + m["sort_ms"] + m["unique_ms"] for m in mets) / len(mets)
     kpos = sum(m["kmer_positions"] for m in mets) / len(mets)
     stages = {"encode_ms": sum(m["encode_ms"] for m in mets) / len(mets),

@@ -839,10 +839,8 @@ bool plan_join(gkd_ctx *c, const HostPairs &hp, uint64_t first, uint64_t count, 
     const bool forced = c->isect_algo == 2;
     const uint32_t lt_min = (uint32_t)std::max(1, c->key_bits - 31), lt_max = (uint32_t)c->key_bits - 1u;
     if (lt_min > lt_max) return false;
-    const uint32_t slots = join_table_slots();
     uint32_t fill_pct = 30;
     if (const char *e = getenv("GKD_JOIN_FILL")) fill_pct = (uint32_t)std::min(45, std::max(5, atoi(e)));
-    const uint64_t fill = std::max<uint64_t>(32, (uint64_t)slots * fill_pct / 100);
 
     // candidate rows and the columns they meet
     std::vector<uint32_t> cand;  // UPPER: set ids; RECT: positions in the row-side id list
@@ -864,6 +862,9 @@ bool plan_join(gkd_ctx *c, const HostPairs &hp, uint64_t first, uint64_t count, 
         n_cols = swapped ? hp.na : hp.nb;
         for (uint32_t i = 0; i < nr; i++) cand.push_back(i);
     }
+    const int cfg = join_pick_cfg((uint32_t)cand.size(), n_cols);
+    const uint64_t R = join_cfg_rows(cfg);
+    const uint64_t fill = std::max<uint64_t>(32, (uint64_t)join_cfg_slots(cfg) * fill_pct / 100);
     auto size_at = [&](uint32_t e) -> uint64_t { return c->genomes[row_ids ? row_ids[e] : e].desc.main.n; };
     uint64_t n_max = 0;
     std::vector<std::pair<uint32_t, uint32_t>> byl;  // (level, entry)
@@ -871,7 +872,7 @@ bool plan_join(gkd_ctx *c, const HostPairs &hp, uint64_t first, uint64_t count, 
         const uint64_t n = size_at(e);
         if (n == 0) continue;  // nothing can match: the counts stay 0
         n_max = std::max(n_max, n);
-        uint32_t L = ceil_log2_u32((uint32_t)std::min<uint64_t>(0xFFFFFFFFull, (32ull * n + fill - 1) / fill));
+        uint32_t L = ceil_log2_u32((uint32_t)std::min<uint64_t>(0xFFFFFFFFull, (R * n + fill - 1) / fill));
         L = std::min(std::max(L, lt_min), lt_max);
         byl.push_back({L, e});
     }
@@ -880,12 +881,13 @@ bool plan_join(gkd_ctx *c, const HostPairs &hp, uint64_t first, uint64_t count, 
         // enough rows to share a probe, enough columns to pay for building the tables, and sets large enough
         // that the tables of the coarsest usable range are not almost empty
         if (byl.size() < 16 || n_cols < 64) return false;
-        if (32ull * n_max < (fill << lt_min) / 4) return false;
+        if (R * n_max < (fill << lt_min) / 4) return false;
     }
     std::stable_sort(byl.begin(), byl.end(), [](const auto &x, const auto &y) { return x.first > y.first; });
     plan = JoinPlan{};
     plan.mode = hp.mode;
     plan.key_bits = c->key_bits;
+    plan.cfg = cfg;
     plan.n_cols = n_cols;
     plan.first = first;
     plan.count = count;
@@ -899,10 +901,10 @@ bool plan_join(gkd_ctx *c, const HostPairs &hp, uint64_t first, uint64_t count, 
         if (plan.n_classes >= (uint32_t)JOIN_MAX_CLASSES) return false;
         JoinClass &k = plan.cls[plan.n_classes++];
         k.level = byl[i].first;
-        k.blk_first = (uint32_t)(rows.size() / 32);
+        k.blk_first = (uint32_t)(rows.size() / R);
         for (size_t t = i; t < j; t++) rows.push_back(byl[t].second);
-        while (rows.size() % 32) rows.push_back(0xFFFFFFFFu);
-        k.n_blocks = (uint32_t)(rows.size() / 32) - k.blk_first;
+        while (rows.size() % R) rows.push_back(0xFFFFFFFFu);
+        k.n_blocks = (uint32_t)(rows.size() / R) - k.blk_first;
         k.task_first = tasks;
         tasks += (unsigned long long)k.n_blocks << k.level;
         i = j;

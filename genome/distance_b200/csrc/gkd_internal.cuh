@@ -249,7 +249,7 @@ cudaError_t launch_intersect(const SetDesc *sets, PairSource src, int use_pal, c
 // kernel 4, block-join form (join.cu): 32 row sets share one shared-memory hash table per key range
 struct JoinClass {          // the row blocks whose sizes call for 2^level key ranges
     uint32_t level;
-    uint32_t blk_first;     // first block of the class in rows[] (block b = rows[32b .. 32b+32))
+    uint32_t blk_first;     // first block of the class in rows[] (block b = rows[R b .. R b + R), R = join_cfg_rows(cfg))
     uint32_t n_blocks;
     uint32_t pad_;
     unsigned long long task_first;  // tasks of the class: n_blocks << level, range-major
@@ -258,18 +258,21 @@ constexpr int JOIN_MAX_CLASSES = 32;
 struct JoinPlan {
     int mode;               // PAIRS_UPPER or PAIRS_RECT
     int key_bits;
+    int cfg;                // geometry index (join_pick_cfg)
     uint32_t n_cols;        // UPPER: number of sets (columns are set ids 0..n-1); RECT: entries of col_ids
     uint32_t n_classes;
     unsigned long long n_tasks;
     unsigned long long first, count;        // UPPER: linear pair range of the call
     unsigned long long stride_r, stride_c;  // RECT: result slot = row position * stride_r + column position * stride_c
-    const uint32_t *rows;     // blocks of 32: UPPER set ids, RECT positions in row_ids; 0xFFFFFFFF pads a class
+    const uint32_t *rows;     // blocks of R rows: UPPER set ids, RECT positions in row_ids; 0xFFFFFFFF pads a class
     const uint32_t *row_ids;  // RECT: ids of the row side; UPPER: nullptr
     const uint32_t *col_ids;  // RECT: ids of the column side; UPPER: nullptr
     JoinClass cls[JOIN_MAX_CLASSES];
 };
 cudaError_t join_configure();    // per-device function attributes
-uint32_t join_table_slots();     // slots of the shared-memory table of the selected configuration
+int join_pick_cfg(uint32_t n_rows, uint32_t n_cols);  // table geometry for a call (GKD_JOIN_CFG pins one)
+uint32_t join_cfg_slots(int cfg);  // slots of the shared-memory table
+uint32_t join_cfg_rows(int cfg);   // rows per block (32 or 64)
 cudaError_t launch_join(const SetDesc *sets, const JoinPlan &plan, uint32_t *counts, unsigned long long *work_counter,
                         uint32_t *err, int n_sms, cudaStream_t s);
 struct EpilogueOut {

@@ -21,8 +21,8 @@
 //   * hits are tallied per row with ballots (lane r keeps the count of row r) and flushed with one
 //     atomicAdd per (row, column, range) that saw a match.
 //
-// Per pair and column key this is 1/32 of a probe instead of a two-pointer merge step, and every set is read
-// once per ROW BLOCK instead of once per row; tasks are enumerated range-major so the column runs of one range
+// Per pair and column key this is 1/32 (1/64 with 64-row blocks: two mask words per slot) of a probe instead of
+// a two-pointer merge step, and every set is read once per ROW BLOCK instead of once per row; tasks are enumerated range-major so the column runs of one range
 // are served from L2 to all row blocks.  Counts are exact (a key's identity inside a range is its low word).
 // Used for 32-bit low words (DNA/RNA K <= 21, protein K <= 5) when a call has enough rows and columns;
 // everything else (lists, greedy pass, 64-bit keys, tiny sets, palindrome sub-sets) stays on the merge kernel.
@@ -75,28 +75,37 @@ __device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {  // shared-window a
     return v;
 }
 
-constexpr int KPT = 6;  // column keys per lane per trip: a run of ~150 keys (30 % fill / 32 rows) is one trip
-
 }  // namespace
 
-template <int SLOTS_LOG2, int THREADS, int CTAS>
+// ROWS = rows per block (32 or 64: one or two mask words per slot), KPT = column keys per lane per trip (a column's
+// run of one range, fill / ROWS keys on average, should fit one trip)
+template <int SLOTS_LOG2, int THREADS, int CTAS, int ROWS, int KPT>
 __global__ void __launch_bounds__(THREADS, CTAS)
     k_join(const SetDesc *__restrict__ sets, JoinPlan plan, uint32_t *__restrict__ counts,
            unsigned long long *__restrict__ work_counter, uint32_t *__restrict__ err) {
     constexpr uint32_t SLOTS = 1u << SLOTS_LOG2, SMASK = SLOTS - 1u;
     constexpr uint32_t MAXFILL = SLOTS / 2u + SLOTS / 8u;
-    constexpr int NW = THREADS / 32;
+    constexpr int NW = THREADS / 32, RW = ROWS / 32;
+    static_assert(ROWS == 32 || ROWS == 64, "one or two mask words per slot");
+    static_assert(THREADS >= ROWS, "one thread per row looks the runs up");
     extern __shared__ __align__(16) uint32_t sm_tab[];
-    uint32_t *keys = sm_tab, *masks = sm_tab + SLOTS;
+    uint32_t *keys = sm_tab, *masks = sm_tab + SLOTS;  // masks: word w of slot s at masks[w * SLOTS + s]
     __shared__ unsigned long long s_task;
-    __shared__ uint32_t s_rowid[32], s_rowpos[32];
-    __shared__ uint32_t s_fill, s_cbeg;
-    __shared__ RangeRun s_run[32];
+    __shared__ uint32_t s_rowid[ROWS], s_rowpos[ROWS];
+    __shared__ uint32_t s_part_fill[RW], s_part_min[RW], s_colgrp;
+    __shared__ RangeRun s_run[ROWS];
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     const uint32_t FULL = 0xffffffffu;
+    // shared-window address of the table, made opaque so it stays in a register instead of being re-derived
+    // from the generic pointer at every probe
+    uint32_t kbase = (uint32_t)__cvta_generic_to_shared(keys);
+    asm volatile("" : "+r"(kbase));
+    constexpr uint32_t M4 = SMASK << 2, MASKS_OFF = SLOTS * 4u;
+    unsigned long long next_task = 0;
+    if (tid == 0) next_task = atomicAdd(work_counter, 1ull);
 
     for (;;) {
-        if (tid == 0) s_task = atomicAdd(work_counter, 1ull);
+        if (tid == 0) s_task = next_task;
         __syncthreads();  // also: every warp is done probing the previous table
         const unsigned long long task = s_task;
         if (task >= plan.n_tasks) return;
@@ -114,39 +123,47 @@ __global__ void __launch_bounds__(THREADS, CTAS)
         {  // clear the table
             uint4 *k4 = (uint4 *)keys, *m4 = (uint4 *)masks;
             const uint4 e4 = make_uint4(EMPTY, EMPTY, EMPTY, EMPTY), z4 = make_uint4(0, 0, 0, 0);
-            for (uint32_t i = tid; i < SLOTS / 4; i += THREADS) {
-                k4[i] = e4;
-                m4[i] = z4;
-            }
+            for (uint32_t i = tid; i < SLOTS / 4; i += THREADS) k4[i] = e4;
+            for (uint32_t i = tid; i < RW * SLOTS / 4; i += THREADS) m4[i] = z4;
         }
-        if (warp == 0) {
-            // lane r looks up row r of the block and its run of this range; the runs' total is checked
+        if (tid < (uint32_t)ROWS) {
+            // thread r looks up row r of the block and its run of this range; the runs' total is checked
             // before anything is inserted, so the table can never fill up
-            const uint32_t pos = plan.rows[(size_t)blk * 32u + lane];
+            const uint32_t pos = plan.rows[(size_t)blk * ROWS + tid];
             uint32_t id = JOIN_INVALID;
             if (pos != JOIN_INVALID) id = plan.row_ids ? plan.row_ids[pos] : pos;
-            s_rowpos[lane] = pos;
-            s_rowid[lane] = id;
+            s_rowpos[tid] = pos;
+            s_rowid[tid] = id;
             RangeRun rr{};
             if (id != JOIN_INVALID) rr = range_run(sets[id].main, L, rho);
-            s_run[lane] = rr;
+            s_run[tid] = rr;
             const uint32_t total = __reduce_add_sync(FULL, rr.hi - rr.lo);
             const uint32_t mn = __reduce_min_sync(FULL, id);
             if (lane == 0) {
-                s_fill = total;
-                s_cbeg = plan.mode == PAIRS_UPPER ? mn + 1u : 0u;  // columns right of the block's first row
+                s_part_fill[warp] = total;
+                s_part_min[warp] = mn;
             }
         }
+        if (tid == 0) s_colgrp = 0;
         __syncthreads();
-
+        uint32_t fill = 0, min_id = JOIN_INVALID;
+#pragma unroll
+        for (int w = 0; w < RW; w++) {
+            fill += s_part_fill[w];
+            min_id = min(min_id, s_part_min[w]);
+        }
         // ---- build: the rows' runs of this range go into the table -------------------------------------
-        if (s_fill > MAXFILL) {
-            if (tid == 0) atomicExch(err, 1u);  // the host redoes the call with the merge kernel
+        if (fill > MAXFILL) {
+            if (tid == 0) {
+                atomicExch(err, 1u);  // the host redoes the call with the merge kernel
+                next_task = atomicAdd(work_counter, 1ull);
+            }
             continue;
         }
-        for (uint32_t r = warp; r < 32u; r += NW) {
+        for (uint32_t r = warp; r < (uint32_t)ROWS; r += NW) {
             const RangeRun rr = s_run[r];
-            const uint32_t bit = 1u << r;
+            const uint32_t bit = 1u << (r & 31u);
+            uint32_t *mw = masks + (r >> 5) * SLOTS;
             for (uint32_t i = rr.lo + lane; i < rr.hi; i += 32u) {
                 const uint32_t k = __ldg(rr.lows + i);
                 if (((k >> fs) & rr.fm) != rr.fv) continue;
@@ -154,7 +171,7 @@ __global__ void __launch_bounds__(THREADS, CTAS)
                 for (;;) {
                     const uint32_t old = atomicCAS(&keys[s], EMPTY, k);
                     if (old == EMPTY || old == k) {
-                        atomicOr(&masks[s], bit);
+                        atomicOr(&mw[s], bit);
                         break;
                     }
                     s = (s + 1u) & SMASK;
@@ -164,24 +181,37 @@ __global__ void __launch_bounds__(THREADS, CTAS)
         __syncthreads();
 
         // ---- probe: stream every column's run of the range ---------------------------------------------
-        // Warp w takes the columns cbeg + w, cbeg + w + NW, ... (related genomes have neighbouring ids, so the
-        // expensive columns spread over all warps); 32 of them are prepared at a time, one per lane, and the
-        // keys of the next column are requested before the current one is probed.  A column's run of a range
-        // (~150 keys at the default fill) fits one trip of KPT keys per lane.
+        // The columns are dealt in groups: group g holds the columns cbeg + g, cbeg + g + G, ... (related genomes
+        // have neighbouring ids, so the expensive columns spread over all groups); a warp takes the next group,
+        // prepares its columns one per lane, and requests the keys of the next column before it probes the
+        // current one.
+        if (tid == 0) next_task = atomicAdd(work_counter, 1ull);  // its latency hides behind the probing
+        const uint32_t cbeg = plan.mode == PAIRS_UPPER ? min_id + 1u : 0u;  // upper triangle: columns right of the first row
         const uint32_t cend = plan.n_cols;
-        const uint32_t my_rowid = s_rowid[lane], my_rowpos = s_rowpos[lane];
-        const uint32_t kbase = (uint32_t)__cvta_generic_to_shared(keys);
-        constexpr uint32_t M4 = SMASK << 2, MASKS_OFF = SLOTS * 4u;
-        for (uint32_t g0 = s_cbeg + warp; g0 < cend; g0 += 32u * NW) {
-            const uint32_t c_mine = g0 + lane * NW;
+        const uint32_t ncols = cend > cbeg ? cend - cbeg : 0u;
+        // about three groups per warp, at most 32 columns each
+        uint32_t G = (ncols + 31u) / 32u;
+        if (G < 3u * NW) G = 3u * NW;
+        if (G > ncols) G = ncols;
+        uint32_t my_rowid[RW], my_rowpos[RW];
+#pragma unroll
+        for (int w = 0; w < RW; w++) {
+            my_rowid[w] = s_rowid[w * 32 + lane];
+            my_rowpos[w] = s_rowpos[w * 32 + lane];
+        }
+        for (;;) {
+            uint32_t g = 0;
+            if (lane == 0) g = atomicAdd(&s_colgrp, 1u);
+            g = __shfl_sync(FULL, g, 0);
+            if (g >= G) break;
+            const uint32_t c_mine = cbeg + g + lane * G;
             uint32_t col_id = 0;
             RangeRun cr{};
             if (c_mine < cend) {
                 col_id = plan.col_ids ? plan.col_ids[c_mine] : c_mine;
                 cr = range_run(sets[col_id].main, L, rho);
             }
-            uint32_t nb = (cend - g0 + NW - 1u) / NW;
-            if (nb > 32u) nb = 32u;
+            const uint32_t nb = (ncols - g + G - 1u) / G;  // columns of this group (<= 32)
             uint32_t nk[KPT], nlo, nhi;
             const uint32_t *nlows;
             auto fetch = [&](uint32_t j) {
@@ -195,6 +225,13 @@ __global__ void __launch_bounds__(THREADS, CTAS)
                 }
             };
             fetch(0);
+            // matches: acc[w][x] holds four 8-bit counters, byte b = row 32w + x + 8b, of THIS lane's keys;
+            // all zero whenever nothing is pending (flush clears them), so columns without a match never touch them
+            uint32_t acc[RW][8];
+#pragma unroll
+            for (int w = 0; w < RW; w++)
+#pragma unroll
+                for (int x = 0; x < 8; x++) acc[w][x] = 0;
             for (uint32_t j = 0; j < nb; j++) {
                 const uint32_t lo = nlo, hi = nhi;
                 const uint32_t *lows = nlows;
@@ -206,83 +243,109 @@ __global__ void __launch_bounds__(THREADS, CTAS)
                 const uint32_t fm = __shfl_sync(FULL, cr.fm, j), fv = __shfl_sync(FULL, cr.fv, j);
                 const uint32_t cid = __shfl_sync(FULL, col_id, j);
                 // rows that form a requested pair with this column (upper triangle: row id < column id)
-                const uint32_t rowmask = plan.mode == PAIRS_UPPER ? __ballot_sync(FULL, my_rowid < cid) : FULL;
-                // matches: acc[g] holds four 8-bit counters, byte b = row g + 8b, of THIS lane's keys
-                uint32_t acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+                uint32_t rowmask[RW];
+#pragma unroll
+                for (int w = 0; w < RW; w++)
+                    rowmask[w] = plan.mode == PAIRS_UPPER ? __ballot_sync(FULL, my_rowid[w] < cid) : FULL;
                 uint32_t pending = 0;  // trips added to acc since the last flush (warp-uniform)
-                uint32_t cnt = 0;      // lane r: matches of row r with this column in this range
+                uint32_t cnt[RW];      // lane r: matches of rows r (, r + 32) with this column in this range
+#pragma unroll
+                for (int w = 0; w < RW; w++) cnt[w] = 0;
                 auto flush = [&]() {
 #pragma unroll
-                    for (int g = 0; g < 8; g++) {
-                        const uint32_t even = __reduce_add_sync(FULL, acc[g] & 0x00FF00FFu);         // rows g, g+16
-                        const uint32_t odd = __reduce_add_sync(FULL, (acc[g] >> 8) & 0x00FF00FFu);   // rows g+8, g+24
-                        const uint32_t v = (lane & 8u) ? odd : even;
-                        if ((lane & 7u) == (uint32_t)g) cnt += (lane & 16u) ? (v >> 16) : (v & 0xFFFFu);
-                        acc[g] = 0;
+                    for (int w = 0; w < RW; w++) {
+#pragma unroll
+                        for (int x = 0; x < 8; x++) {
+                            const uint32_t even = __reduce_add_sync(FULL, acc[w][x] & 0x00FF00FFu);        // rows x, x+16
+                            const uint32_t odd = __reduce_add_sync(FULL, (acc[w][x] >> 8) & 0x00FF00FFu);  // rows x+8, x+24
+                            const uint32_t v = (lane & 8u) ? odd : even;
+                            if ((lane & 7u) == (uint32_t)x) cnt[w] += (lane & 16u) ? (v >> 16) : (v & 0xFFFFu);
+                            acc[w][x] = 0;
+                        }
                     }
                     pending = 0;
                 };
                 for (uint32_t base = lo; base < hi; base += 32u * KPT) {
-                    uint32_t m[KPT], anym = 0;
+                    uint32_t m[RW][KPT], anym = 0;
 #pragma unroll
                     for (int q = 0; q < KPT; q++) {
                         const uint32_t i = base + q * 32u + lane;
                         if (base != lo) k[q] = i < hi ? __ldg(lows + i) : 0u;
                         const bool ok = i < hi && ((k[q] >> fs) & fm) == fv;
-                        uint32_t a = kbase + (((k[q] * 0x9E3779B1u) >> (30 - SLOTS_LOG2)) & M4);
-                        uint32_t e = ok ? lds_u32(a) : EMPTY;
+                        // every lane loads (lanes without a key probe slot hash(0), a broadcast) so the probe is
+                        // branch-free; an empty slot carries mask 0, so a stray hit on it counts nothing
+                        uint32_t off = ((k[q] * 0x9E3779B1u) >> (30 - SLOTS_LOG2)) & M4;
+                        uint32_t e = lds_u32(kbase + off);
+                        e = ok ? e : EMPTY;
                         while (e != k[q] && e != EMPTY) {
-                            a = kbase + ((a - kbase + 4u) & M4);
-                            e = lds_u32(a);
+                            off = (off + 4u) & M4;
+                            e = lds_u32(kbase + off);
                         }
-                        m[q] = (ok && e == k[q]) ? (lds_u32(a + MASKS_OFF) & rowmask) : 0u;
-                        anym |= m[q];
+                        const bool hit = ok && e == k[q];
+#pragma unroll
+                        for (int w = 0; w < RW; w++) {
+                            const uint32_t mv = lds_u32(kbase + off + MASKS_OFF * (1u + w));
+                            m[w][q] = hit ? (mv & rowmask[w]) : 0u;
+                            anym |= m[w][q];
+                        }
                     }
                     if (__any_sync(FULL, anym != 0u)) {
 #pragma unroll
-                        for (int q = 0; q < KPT; q++) {
+                        for (int w = 0; w < RW; w++)
 #pragma unroll
-                            for (int g = 0; g < 8; g++) acc[g] += (m[q] >> g) & 0x01010101u;
-                        }
+                            for (int q = 0; q < KPT; q++)
+#pragma unroll
+                                for (int x = 0; x < 8; x++) acc[w][x] += (m[w][q] >> x) & 0x01010101u;
                         if (++pending == 255u / KPT) flush();  // before a byte counter can overflow
                     }
                 }
                 if (pending) flush();
-                if (cnt) {
+#pragma unroll
+                for (int w = 0; w < RW; w++) {
+                    if (!cnt[w]) continue;
                     unsigned long long t;
                     bool valid = true;
                     if (plan.mode == PAIRS_UPPER) {
-                        const unsigned long long i = my_rowid, n = plan.n_cols;
+                        const unsigned long long i = my_rowid[w], n = plan.n_cols;
                         t = i * (2ull * n - i - 1ull) / 2ull + ((unsigned long long)cid - i - 1ull) - plan.first;
                         valid = t < plan.count;  // pairs before `first` wrap around to huge values
                     } else {
-                        t = (unsigned long long)my_rowpos * plan.stride_r + (unsigned long long)(g0 + j * NW) * plan.stride_c;
+                        t = (unsigned long long)my_rowpos[w] * plan.stride_r +
+                            (unsigned long long)(cbeg + g + j * G) * plan.stride_c;
                     }
-                    if (valid) atomicAdd(&counts[t], cnt);
+                    if (valid) atomicAdd(&counts[t], cnt[w]);
                 }
             }
         }
     }
 }
 
-// Table geometries: <log2 slots, threads per CTA, CTAs per SM>; keys + masks = 8 bytes per slot
-#define GKD_FOR_EACH_JCFG(X) X(0, 14, 1024, 1) X(1, 13, 320, 3) X(2, 13, 256, 3) X(3, 14, 512, 1) X(4, 12, 160, 6) X(5, 12, 128, 6) X(6, 13, 512, 2) X(7, 12, 256, 4)
+// Geometries: <log2 slots, threads per CTA, CTAs per SM, rows per block, keys per lane per trip>; a slot is a
+// 4-byte key plus one 4-byte mask word per 32 rows
+#define GKD_FOR_EACH_JCFG(X)                                                                                   \
+    X(0, 14, 1024, 1, 64, 3) X(1, 14, 1024, 1, 32, 6) X(2, 13, 512, 2, 32, 3) X(3, 14, 512, 1, 64, 3) X(4, 13, 512, 2, 64, 2) \
+    X(5, 12, 256, 4, 32, 2) X(6, 14, 1024, 1, 64, 4) X(7, 14, 768, 1, 64, 3)
 constexpr int N_JCFG = 8;
-constexpr int DEFAULT_JCFG = 0;
-static const int g_jcfg_slots_log2[N_JCFG] = {14, 13, 13, 14, 12, 12, 13, 12};
+static const int g_jcfg_slots_log2[N_JCFG] = {14, 14, 13, 14, 13, 12, 14, 14};
+static const int g_jcfg_rows[N_JCFG] = {64, 32, 32, 64, 64, 32, 64, 64};
 
-static int env_jcfg() {
-    const char *e = getenv("GKD_JOIN_CFG");
-    int c = e ? atoi(e) : DEFAULT_JCFG;
-    return (c < 0 || c >= N_JCFG) ? DEFAULT_JCFG : c;
+// GKD_JOIN_CFG pins a geometry; otherwise 64-row blocks when the call has enough rows and columns to fill them
+// (measured on the B200: 64 rows win from ~500 columns on, 32 rows below), 32-row blocks else
+int join_pick_cfg(uint32_t n_rows, uint32_t n_cols) {
+    if (const char *e = getenv("GKD_JOIN_CFG")) {
+        const int c = atoi(e);
+        if (c >= 0 && c < N_JCFG) return c;
+    }
+    return (n_rows >= 192 && n_cols >= 448) ? 0 : 1;
 }
-
-uint32_t join_table_slots() { return 1u << g_jcfg_slots_log2[env_jcfg()]; }
+uint32_t join_cfg_slots(int cfg) { return 1u << g_jcfg_slots_log2[cfg]; }
+uint32_t join_cfg_rows(int cfg) { return (uint32_t)g_jcfg_rows[cfg]; }
 
 cudaError_t join_configure() {
     cudaError_t e;
-#define X(i, SL, T, C)                                                                                              \
-    if ((e = cudaFuncSetAttribute(k_join<SL, T, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (8 << SL))) != cudaSuccess) \
+#define X(i, SL, T, C, R, K)                                                                                   \
+    if ((e = cudaFuncSetAttribute(k_join<SL, T, C, R, K>, cudaFuncAttributeMaxDynamicSharedMemorySize,        \
+                                  (4 << SL) * (1 + R / 32))) != cudaSuccess)                                   \
         return e;
     GKD_FOR_EACH_JCFG(X)
 #undef X
@@ -294,13 +357,13 @@ cudaError_t launch_join(const SetDesc *sets, const JoinPlan &plan, uint32_t *cou
     if (plan.n_tasks == 0) return cudaSuccess;
     cudaError_t e = cudaMemsetAsync(work_counter, 0, sizeof(unsigned long long), s);
     if (e != cudaSuccess) return e;
-    const int c = env_jcfg();
-#define X(i, SL, T, C)                                                                           \
-    if (c == i) {                                                                                \
-        unsigned long long grid = (unsigned long long)n_sms * C;                                 \
-        if (grid > plan.n_tasks) grid = plan.n_tasks;                                            \
-        k_join<SL, T, C><<<(unsigned)grid, T, (8 << SL), s>>>(sets, plan, counts, work_counter, err); \
-        return cudaGetLastError();                                                               \
+    const int c = plan.cfg;
+#define X(i, SL, T, C, R, K)                                                                                    \
+    if (c == i) {                                                                                               \
+        unsigned long long grid = (unsigned long long)n_sms * C;                                                \
+        if (grid > plan.n_tasks) grid = plan.n_tasks;                                                           \
+        k_join<SL, T, C, R, K><<<(unsigned)grid, T, (4 << SL) * (1 + R / 32), s>>>(sets, plan, counts, work_counter, err); \
+        return cudaGetLastError();                                                                              \
     }
     GKD_FOR_EACH_JCFG(X)
 #undef X
