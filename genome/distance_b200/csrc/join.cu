@@ -90,10 +90,16 @@ __global__ void __launch_bounds__(THREADS, CTAS)
     static_assert(THREADS >= ROWS, "one thread per row looks the runs up");
     extern __shared__ __align__(16) uint32_t sm_tab[];
     uint32_t *keys = sm_tab, *masks = sm_tab + SLOTS;  // masks: word w of slot s at masks[w * SLOTS + s]
-    __shared__ unsigned long long s_task;
-    __shared__ uint32_t s_rowid[ROWS], s_rowpos[ROWS];
-    __shared__ uint32_t s_part_fill[RW], s_part_min[RW], s_colgrp;
-    __shared__ RangeRun s_run[ROWS];
+    // Everything a task needs before its table can be built, looked up by warp 0 WHILE the other warps still probe
+    // the previous task's table (the look-ups are a chain of dependent global loads): double-buffered.
+    struct TaskInfo {
+        unsigned long long task;
+        uint32_t level, rho, fill, min_id;
+        uint32_t rowid[ROWS], rowpos[ROWS];
+        RangeRun run[ROWS];
+    };
+    __shared__ TaskInfo s_ti[2];
+    __shared__ uint32_t s_colgrp;
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     const uint32_t FULL = 0xffffffffu;
     // shared-window address of the table, made opaque so it stays in a register instead of being re-derived
@@ -101,13 +107,13 @@ __global__ void __launch_bounds__(THREADS, CTAS)
     uint32_t kbase = (uint32_t)__cvta_generic_to_shared(keys);
     asm volatile("" : "+r"(kbase));
     constexpr uint32_t M4 = SMASK << 2, MASKS_OFF = SLOTS * 4u;
-    unsigned long long next_task = 0;
-    if (tid == 0) next_task = atomicAdd(work_counter, 1ull);
 
-    for (;;) {
-        if (tid == 0) s_task = next_task;
-        __syncthreads();  // also: every warp is done probing the previous table
-        const unsigned long long task = s_task;
+    // warp 0: take the next task from the global counter and look up its rows and their runs
+    auto prepare = [&](TaskInfo &ti) {
+        unsigned long long task = 0;
+        if (lane == 0) task = atomicAdd(work_counter, 1ull);
+        task = __shfl_sync(FULL, task, 0);
+        if (lane == 0) ti.task = task;
         if (task >= plan.n_tasks) return;
         // task -> (class, range, row block); range-major inside a class
         uint32_t ci = 0;
@@ -116,77 +122,91 @@ __global__ void __launch_bounds__(THREADS, CTAS)
         const unsigned long long local = task - plan.cls[ci].task_first;
         const uint32_t rho = (uint32_t)(local / plan.cls[ci].n_blocks);
         const uint32_t blk = plan.cls[ci].blk_first + (uint32_t)(local % plan.cls[ci].n_blocks);
+        uint32_t total = 0, mn = JOIN_INVALID;
+#pragma unroll
+        for (int w = 0; w < RW; w++) {
+            const uint32_t r = w * 32u + lane;
+            const uint32_t pos = plan.rows[(size_t)blk * ROWS + r];
+            uint32_t id = JOIN_INVALID;
+            if (pos != JOIN_INVALID) id = plan.row_ids ? plan.row_ids[pos] : pos;
+            ti.rowpos[r] = pos;
+            ti.rowid[r] = id;
+            RangeRun rr{};
+            if (id != JOIN_INVALID) rr = range_run(sets[id].main, L, rho);
+            ti.run[r] = rr;
+            total += rr.hi - rr.lo;
+            mn = min(mn, id);
+        }
+        total = __reduce_add_sync(FULL, total);
+        mn = __reduce_min_sync(FULL, mn);
+        if (lane == 0) {
+            ti.level = L;
+            ti.rho = rho;
+            ti.fill = total;  // checked before anything is inserted, so the table can never fill up
+            ti.min_id = mn;
+        }
+    };
+    if (warp == 0) prepare(s_ti[0]);
+
+    for (uint32_t p = 0;; p ^= 1u) {
+        __syncthreads();  // s_ti[p] is ready, and every warp is done probing the previous table
+        const TaskInfo &ti = s_ti[p];
+        if (ti.task >= plan.n_tasks) return;
+        const uint32_t L = ti.level, rho = ti.rho;
         const uint32_t fs = (uint32_t)plan.key_bits - L;  // 1..31: low-word bits below the range index
         // no key of the range has this low word: bit 31 lies inside the range index and is flipped
         const uint32_t EMPTY = ((uint32_t)((unsigned long long)rho << fs)) ^ 0x80000000u;
-
+        const bool overfull = ti.fill > MAXFILL;
+        if (overfull && tid == 0) atomicExch(err, 1u);  // the host redoes the call with the merge kernel
         {  // clear the table
             uint4 *k4 = (uint4 *)keys, *m4 = (uint4 *)masks;
             const uint4 e4 = make_uint4(EMPTY, EMPTY, EMPTY, EMPTY), z4 = make_uint4(0, 0, 0, 0);
             for (uint32_t i = tid; i < SLOTS / 4; i += THREADS) k4[i] = e4;
             for (uint32_t i = tid; i < RW * SLOTS / 4; i += THREADS) m4[i] = z4;
         }
-        if (tid < (uint32_t)ROWS) {
-            // thread r looks up row r of the block and its run of this range; the runs' total is checked
-            // before anything is inserted, so the table can never fill up
-            const uint32_t pos = plan.rows[(size_t)blk * ROWS + tid];
-            uint32_t id = JOIN_INVALID;
-            if (pos != JOIN_INVALID) id = plan.row_ids ? plan.row_ids[pos] : pos;
-            s_rowpos[tid] = pos;
-            s_rowid[tid] = id;
-            RangeRun rr{};
-            if (id != JOIN_INVALID) rr = range_run(sets[id].main, L, rho);
-            s_run[tid] = rr;
-            const uint32_t total = __reduce_add_sync(FULL, rr.hi - rr.lo);
-            const uint32_t mn = __reduce_min_sync(FULL, id);
-            if (lane == 0) {
-                s_part_fill[warp] = total;
-                s_part_min[warp] = mn;
-            }
-        }
         if (tid == 0) s_colgrp = 0;
         __syncthreads();
-        uint32_t fill = 0, min_id = JOIN_INVALID;
-#pragma unroll
-        for (int w = 0; w < RW; w++) {
-            fill += s_part_fill[w];
-            min_id = min(min_id, s_part_min[w]);
-        }
+
         // ---- build: the rows' runs of this range go into the table -------------------------------------
-        if (fill > MAXFILL) {
-            if (tid == 0) {
-                atomicExch(err, 1u);  // the host redoes the call with the merge kernel
-                next_task = atomicAdd(work_counter, 1ull);
-            }
-            continue;
-        }
-        for (uint32_t r = warp; r < (uint32_t)ROWS; r += NW) {
-            const RangeRun rr = s_run[r];
+        // a warp per row; the keys of a row are requested KB per lane at a time before any is inserted
+        constexpr int KB = 192 / ROWS;  // a row's run is ~fill / ROWS keys: one batch
+        for (uint32_t r = warp; r < (uint32_t)ROWS && !overfull; r += NW) {
+            const RangeRun rr = ti.run[r];
             const uint32_t bit = 1u << (r & 31u);
             uint32_t *mw = masks + (r >> 5) * SLOTS;
-            for (uint32_t i = rr.lo + lane; i < rr.hi; i += 32u) {
-                const uint32_t k = __ldg(rr.lows + i);
-                if (((k >> fs) & rr.fm) != rr.fv) continue;
-                uint32_t s = join_hash<SLOTS_LOG2>(k);
-                for (;;) {
-                    const uint32_t old = atomicCAS(&keys[s], EMPTY, k);
-                    if (old == EMPTY || old == k) {
-                        atomicOr(&mw[s], bit);
-                        break;
+            for (uint32_t base = rr.lo; base < rr.hi; base += 32u * KB) {
+                uint32_t kk[KB];
+#pragma unroll
+                for (int q = 0; q < KB; q++) {
+                    const uint32_t i = base + q * 32u + lane;
+                    kk[q] = i < rr.hi ? __ldg(rr.lows + i) : 0u;
+                }
+#pragma unroll
+                for (int q = 0; q < KB; q++) {
+                    const uint32_t i = base + q * 32u + lane;
+                    if (i >= rr.hi || ((kk[q] >> fs) & rr.fm) != rr.fv) continue;
+                    uint32_t s = join_hash<SLOTS_LOG2>(kk[q]);
+                    for (;;) {
+                        const uint32_t old = atomicCAS(&keys[s], EMPTY, kk[q]);
+                        if (old == EMPTY || old == kk[q]) {
+                            atomicOr(&mw[s], bit);
+                            break;
+                        }
+                        s = (s + 1u) & SMASK;
                     }
-                    s = (s + 1u) & SMASK;
                 }
             }
         }
         __syncthreads();
+        if (warp == 0) prepare(s_ti[p ^ 1u]);  // the next task's look-ups hide behind the other warps' probing
+        if (overfull) continue;
 
         // ---- probe: stream every column's run of the range ---------------------------------------------
         // The columns are dealt in groups: group g holds the columns cbeg + g, cbeg + g + G, ... (related genomes
         // have neighbouring ids, so the expensive columns spread over all groups); a warp takes the next group,
         // prepares its columns one per lane, and requests the keys of the next column before it probes the
         // current one.
-        if (tid == 0) next_task = atomicAdd(work_counter, 1ull);  // its latency hides behind the probing
-        const uint32_t cbeg = plan.mode == PAIRS_UPPER ? min_id + 1u : 0u;  // upper triangle: columns right of the first row
+        const uint32_t cbeg = plan.mode == PAIRS_UPPER ? ti.min_id + 1u : 0u;  // upper triangle: columns right of the first row
         const uint32_t cend = plan.n_cols;
         const uint32_t ncols = cend > cbeg ? cend - cbeg : 0u;
         // about three groups per warp, at most 32 columns each
@@ -196,8 +216,8 @@ __global__ void __launch_bounds__(THREADS, CTAS)
         uint32_t my_rowid[RW], my_rowpos[RW];
 #pragma unroll
         for (int w = 0; w < RW; w++) {
-            my_rowid[w] = s_rowid[w * 32 + lane];
-            my_rowpos[w] = s_rowpos[w * 32 + lane];
+            my_rowid[w] = ti.rowid[w * 32 + lane];
+            my_rowpos[w] = ti.rowpos[w * 32 + lane];
         }
         for (;;) {
             uint32_t g = 0;
@@ -336,7 +356,7 @@ int join_pick_cfg(uint32_t n_rows, uint32_t n_cols) {
         const int c = atoi(e);
         if (c >= 0 && c < N_JCFG) return c;
     }
-    return (n_rows >= 192 && n_cols >= 448) ? 0 : 1;
+    return (n_rows >= 192 && n_cols >= 448) ? 7 : 1;
 }
 uint32_t join_cfg_slots(int cfg) { return 1u << g_jcfg_slots_log2[cfg]; }
 uint32_t join_cfg_rows(int cfg) { return (uint32_t)g_jcfg_rows[cfg]; }

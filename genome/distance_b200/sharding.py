@@ -129,11 +129,17 @@ def plan_panels(meta, lo: int, hi: int, max_sets: int):
 
 
 def ring_all_vs_all(eng, n_genomes: int, world: int, rank: int, device, panel_genomes: int = 128, sink=None,
-                    stats=None):
+                    stats=None, group_sets: int = 1024):
     """All-vs-all across `world` ranks (see the section comment).  `eng` holds this rank's genome slice
     as built sets 0..m-1 and provides arena_meta / arena_view / adopt_sets / all_vs_all_range /
     query_vs_ref / truncate.  `sink(gi, gj, inter, dist)` receives every block (global ids, row-major);
-    by default the blocks are collected and returned as (gi, gj, inter, dist) with gi < gj."""
+    by default the blocks are collected and returned as (gi, gj, inter, dist) with gi < gj.
+
+    Panels are the unit of TRANSFER; the unit of COMPUTE is a group of consecutive panels that meet the same
+    rows, up to `group_sets` sets (they may come from several peers): kernel 4's block join builds one table
+    per (64 rows, key range) and probes every column of the call with it, so a call with many columns
+    amortises the tables.  The transfers of group g+1 are in flight while group g is computed, so at most
+    two groups of received sets are resident beside the rank's own slice."""
     import time
 
     import torch
@@ -199,9 +205,28 @@ def ring_all_vs_all(eng, n_genomes: int, world: int, rank: int, device, panel_ge
             torch.cuda.current_stream().synchronize()  # only what this stream waits for: the slot's transfer
         t_wait += time.perf_counter() - t0
 
-    cur = post(slots[0]) if slots else None
+    # compute groups: consecutive slots with the same rows, at most group_sets received sets together
+    groups, cur_g, cur_cols = [], [], 0
+    for idx, slot in enumerate(slots):
+        n_recv = slot[2]["count"] if slot[2] is not None else 0
+        if cur_g and (slots[cur_g[0]][4] != slot[4] or cur_cols + n_recv > max(1, group_sets)):
+            groups.append(cur_g)
+            cur_g, cur_cols = [], 0
+        cur_g.append(idx)
+        cur_cols += n_recv
+    if cur_g:
+        groups.append(cur_g)
 
-    # diagonal block: my genomes against each other (runs while the first panel is in flight)
+    posted = {}
+
+    def post_group(g):
+        for idx in g:
+            posted[idx] = post(slots[idx])
+
+    if groups:
+        post_group(groups[0])
+
+    # diagonal block: my genomes against each other (runs while the first group is in flight)
     if m >= 2:
         cnt = m * (m - 1) // 2
         inter, d = eng.all_vs_all_range(m, 0, cnt)
@@ -209,26 +234,38 @@ def ring_all_vs_all(eng, n_genomes: int, world: int, rank: int, device, panel_ge
         base = mine[0]
         emit(a.astype(np.int64) + base, b.astype(np.int64) + base, inter, d)
 
-    for k, slot in enumerate(slots):
-        nxt = post(slots[k + 1]) if k + 1 < len(slots) else None  # in flight while panel k is intersected
-        reqs, buf, keep = cur
-        finish(reqs)
-        send_p, dst, recv_p, src, rows, theirs = slot
-        if recv_p is not None and rows[1] > rows[0]:
-            first = eng.adopt_sets(buf, recv_p["table"])
-            cols = np.arange(first, first + recv_p["count"], dtype=np.uint32)
+    for gi_, g in enumerate(groups):
+        if gi_ + 1 < len(groups):
+            post_group(groups[gi_ + 1])  # in flight while this group is intersected
+        rows = slots[g[0]][4]
+        parts, bufs, cols = [], [], []
+        for idx in g:
+            reqs, buf, keep = posted.pop(idx)
+            finish(reqs)
+            send_p, dst, recv_p, src, _, theirs = slots[idx]
+            bufs.append((buf, keep))
+            if recv_p is not None and rows[1] > rows[0]:
+                first = eng.adopt_sets(buf, recv_p["table"])
+                cols.append(np.arange(first, first + recv_p["count"], dtype=np.uint32))
+                parts.append((recv_p["count"], theirs[recv_p["first"]:recv_p["first"] + recv_p["count"]]))
+        if cols:
             my_rows = np.arange(rows[0], rows[1], dtype=np.uint32)
-            inter, d = eng.query_vs_ref(my_rows, cols)
-            chunk = theirs[recv_p["first"]:recv_p["first"] + recv_p["count"]]
-            rows_g = np.repeat(np.asarray(mine[rows[0]:rows[1]], dtype=np.int64), len(chunk))
-            cols_g = np.tile(np.asarray(chunk, dtype=np.int64), len(my_rows))
-            emit(rows_g, cols_g, inter, d)
+            inter, d = eng.query_vs_ref(my_rows, np.concatenate(cols))
+            inter = np.asarray(inter).reshape(len(my_rows), -1)
+            d = np.asarray(d).reshape(len(my_rows), -1)
+            off = 0
+            for count, chunk in parts:
+                rows_g = np.repeat(np.asarray(mine[rows[0]:rows[1]], dtype=np.int64), len(chunk))
+                cols_g = np.tile(np.asarray(chunk, dtype=np.int64), len(my_rows))
+                emit(rows_g, cols_g, np.ascontiguousarray(inter[:, off:off + count]).reshape(-1),
+                     np.ascontiguousarray(d[:, off:off + count]).reshape(-1))
+                off += count
             eng.truncate(m)
-        del buf, keep
-        cur = nxt
+        del bufs
     if stats is not None:
         stats["exposed_wait_s"] = t_wait
         stats["slots"] = len(slots)
+        stats["groups"] = len(groups)
     if sink is not None:
         return None
     if not out_i:

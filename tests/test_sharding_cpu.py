@@ -156,7 +156,7 @@ def test_plan_panels_is_a_partition():
             assert (p["table"]["lows_off"] - p["table"]["offs_off"] == 32).all()
 
 
-def _ring_worker(rank, world, port, n, length, k, panel, ret):
+def _ring_worker(rank, world, port, n, length, k, panel, group, ret):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -166,17 +166,20 @@ def _ring_worker(rank, world, port, n, length, k, panel, ret):
     mine = sharding.genome_slice(n, world, rank)
     eng = _CpuPanelEngine(orc, [seqs[g] for g in mine], k)
     stats = {}
-    gi, gj, inter, d = sharding.ring_all_vs_all(eng, n, world, rank, torch.device("cpu"), panel_genomes=panel, stats=stats)
+    gi, gj, inter, d = sharding.ring_all_vs_all(eng, n, world, rank, torch.device("cpu"), panel_genomes=panel, stats=stats,
+                                                 group_sets=group)
+    assert stats["groups"] <= stats["slots"]
     assert len(eng.sets) == len(mine)  # every received panel was dropped again
     ret.put((rank, gi.tolist(), gj.tolist(), [int(x) for x in inter], d.tolist()))
     dist.barrier()
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,panel", [(2, 2), (3, 1), (4, 3)])
-def test_ring_all_vs_all_over_gloo(orc, world, panel):
+@pytest.mark.parametrize("world,panel,group", [(2, 2, 1024), (3, 1, 2), (4, 3, 1), (4, 1, 1024)])
+def test_ring_all_vs_all_over_gloo(orc, world, panel, group):
     """world_size 2-4 on CPU: panels planned from the owners' arena layouts, moved with send/recv, adopted,
-    intersected and dropped; every pair computed exactly once and equal to the oracle"""
+    intersected in groups of up to `group` sets (several panels, possibly of several peers, per call) and
+    dropped; every pair computed exactly once and equal to the oracle"""
     n, length, k = 9, 12000, 15
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
@@ -184,7 +187,7 @@ def test_ring_all_vs_all_over_gloo(orc, world, panel):
     s.close()
     ctx = mp.get_context("spawn")
     ret = ctx.Queue()
-    procs = [ctx.Process(target=_ring_worker, args=(r, world, port, n, length, k, panel, ret), daemon=True)
+    procs = [ctx.Process(target=_ring_worker, args=(r, world, port, n, length, k, panel, group, ret), daemon=True)
              for r in range(world)]
     for p in procs:
         p.start()

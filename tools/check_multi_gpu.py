@@ -26,6 +26,9 @@ def main():
         t = torch.empty(length if g % 5 else length // 7, dtype=torch.uint8, device=dev)
         gkd.synth(t, 17, g % 3, g // 3, 0.02 if g // 3 else 0.0, device=local)
         seqs.append(t)
+    # the single-GPU answer comes from the bucket-merge kernel, the ring runs the block join on every block
+    # (GKD_ISECT_ALGO is read when a context is created): the two kernel-4 forms check each other
+    os.environ["GKD_ISECT_ALGO"] = "merge"
     with gkd.Engine(k=k, device=local) as ref:
         for s in seqs:
             ref.add(s)
@@ -35,6 +38,7 @@ def main():
     mine = sharding.genome_slice(n, world, rank)
     ok = True
     # panel ring: no rank ever holds more than its slice plus two panels; tiny workspace -> several arenas
+    os.environ["GKD_ISECT_ALGO"] = os.environ.get("GKD_CHECK_RING_ALGO", "join")
     with gkd.Engine(k=k, device=local, workspace_bytes=24 << 20) as eng:
         for g in mine:
             eng.add(seqs[g])
