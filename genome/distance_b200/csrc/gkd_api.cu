@@ -834,10 +834,12 @@ void host_pair_ids(const HostPairs &hp, uint64_t t, uint32_t &a, uint32_t &b) {
 bool plan_join(gkd_ctx *c, const HostPairs &hp, uint64_t first, uint64_t count, JoinPlan &plan, std::vector<uint32_t> &rows,
                bool &swapped) {
     swapped = false;
-    if (c->isect_algo == 1 || c->low_bits != 32 || count == 0) return false;
+    if (c->isect_algo == 1 || count == 0) return false;
     if (hp.mode != PAIRS_UPPER && hp.mode != PAIRS_RECT) return false;
     const bool forced = c->isect_algo == 2;
-    const uint32_t lt_min = (uint32_t)std::max(1, c->key_bits - 31), lt_max = (uint32_t)c->key_bits - 1u;
+    // 32-bit low words identify a key only inside a range of at most 2^31 values; 64-bit keys are stored whole
+    const uint32_t lt_min = c->low_bits == 32 ? (uint32_t)std::max(1, c->key_bits - 31) : 1u;
+    const uint32_t lt_max = std::min<uint32_t>((uint32_t)c->key_bits - 1u, 30u);
     if (lt_min > lt_max) return false;
     uint32_t fill_pct = 30;
     if (const char *e = getenv("GKD_JOIN_FILL")) fill_pct = (uint32_t)std::min(45, std::max(5, atoi(e)));
@@ -862,7 +864,7 @@ bool plan_join(gkd_ctx *c, const HostPairs &hp, uint64_t first, uint64_t count, 
         n_cols = swapped ? hp.na : hp.nb;
         for (uint32_t i = 0; i < nr; i++) cand.push_back(i);
     }
-    const int cfg = join_pick_cfg((uint32_t)cand.size(), n_cols);
+    const int cfg = join_pick_cfg((uint32_t)cand.size(), n_cols, c->low_bits);
     const uint64_t R = join_cfg_rows(cfg);
     const uint64_t fill = std::max<uint64_t>(32, (uint64_t)join_cfg_slots(cfg) * fill_pct / 100);
     auto size_at = [&](uint32_t e) -> uint64_t { return c->genomes[row_ids ? row_ids[e] : e].desc.main.n; };

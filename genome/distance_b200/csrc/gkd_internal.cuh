@@ -270,7 +270,7 @@ struct JoinPlan {
     JoinClass cls[JOIN_MAX_CLASSES];
 };
 cudaError_t join_configure();    // per-device function attributes
-int join_pick_cfg(uint32_t n_rows, uint32_t n_cols);  // table geometry for a call (GKD_JOIN_CFG pins one)
+int join_pick_cfg(uint32_t n_rows, uint32_t n_cols, int low_bits);  // table geometry for a call (GKD_JOIN_CFG pins one)
 uint32_t join_cfg_slots(int cfg);  // slots of the shared-memory table
 uint32_t join_cfg_rows(int cfg);   // rows per block (32 or 64)
 cudaError_t launch_join(const SetDesc *sets, const JoinPlan &plan, uint32_t *counts, unsigned long long *work_counter,

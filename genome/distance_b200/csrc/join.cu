@@ -24,8 +24,9 @@
 // Per pair and column key this is 1/32 (1/64 with 64-row blocks: two mask words per slot) of a probe instead of
 // a two-pointer merge step, and every set is read once per ROW BLOCK instead of once per row; tasks are enumerated range-major so the column runs of one range
 // are served from L2 to all row blocks.  Counts are exact (a key's identity inside a range is its low word).
-// Used for 32-bit low words (DNA/RNA K <= 21, protein K <= 5) when a call has enough rows and columns;
-// everything else (lists, greedy pass, 64-bit keys, tiny sets, palindrome sub-sets) stays on the merge kernel.
+// Serves 32-bit low words (DNA/RNA K <= 21, protein K <= 5) and 64-bit keys (the table then holds the whole h) when a
+// call has enough rows and columns; everything else (lists, greedy pass, tiny sets, thin slices, palindrome sub-sets)
+// stays on the merge kernel.
 #include <cstdlib>
 
 #include "gkd_internal.cuh"
@@ -38,14 +39,17 @@ constexpr uint32_t JOIN_INVALID = 0xFFFFFFFFu;
 
 // where set S keeps the keys of range rho (level L): run [lo, hi) of its low words, plus a value filter
 // when the set's own table is coarser than the range (fm == 0: every key of the run is in the range)
+template <typename KT>
 struct RangeRun {
-    const uint32_t *lows;
-    uint32_t lo, hi, fm, fv;
+    const KT *lows;
+    uint32_t lo, hi;
+    KT fm, fv;
 };
 
-__device__ __forceinline__ RangeRun range_run(const SubSet &S, uint32_t L, uint32_t rho) {
-    RangeRun r;
-    r.lows = (const uint32_t *)S.lows;
+template <typename KT>
+__device__ __forceinline__ RangeRun<KT> range_run(const SubSet &S, uint32_t L, uint32_t rho) {
+    RangeRun<KT> r;
+    r.lows = (const KT *)S.lows;
     r.lo = r.hi = 0;
     r.fm = r.fv = 0;
     if (S.n == 0) return r;
@@ -58,28 +62,48 @@ __device__ __forceinline__ RangeRun range_run(const SubSet &S, uint32_t L, uint3
         const uint32_t c = rho >> d;
         r.lo = __ldg(S.offs + c);
         r.hi = __ldg(S.offs + c + 1);
-        r.fm = (1u << d) - 1u;
-        r.fv = rho & r.fm;
+        r.fm = (KT)(((unsigned long long)1 << d) - 1ull);
+        r.fv = (KT)rho & r.fm;
     }
     return r;
 }
 
+// slot * 4 of a key (the byte offset of its mask word; the key word is at the same offset for 32-bit keys, twice
+// that for 64-bit keys)
 template <int SLOTS_LOG2>
-__device__ __forceinline__ uint32_t join_hash(uint32_t k) {
-    return (k * 0x9E3779B1u) >> (32 - SLOTS_LOG2);
+__device__ __forceinline__ uint32_t join_off4(uint32_t k) {
+    return ((k * 0x9E3779B1u) >> (30 - SLOTS_LOG2)) & (((1u << SLOTS_LOG2) - 1u) << 2);
+}
+template <int SLOTS_LOG2>
+__device__ __forceinline__ uint32_t join_off4(uint64_t k) {
+    return (uint32_t)((k * 0x9E3779B97F4A7C15ull) >> (62 - SLOTS_LOG2)) & (((1u << SLOTS_LOG2) - 1u) << 2);
 }
 
-__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {  // shared-window address: no generic-pointer set-up per load
+// shared-window addresses: no generic-pointer set-up per load
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
     uint32_t v;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
     return v;
 }
+__device__ __forceinline__ uint32_t lds_key(uint32_t kbase, uint32_t off4, uint32_t) { return lds_u32(kbase + off4); }
+__device__ __forceinline__ uint64_t lds_key(uint32_t kbase, uint32_t off4, uint64_t) {
+    uint64_t v;
+    asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(kbase + 2u * off4));
+    return v;
+}
+__device__ __forceinline__ uint32_t cas_key(uint32_t *p, uint32_t cmp, uint32_t v) { return atomicCAS(p, cmp, v); }
+__device__ __forceinline__ uint64_t cas_key(uint64_t *p, uint64_t cmp, uint64_t v) {
+    return atomicCAS((unsigned long long *)p, (unsigned long long)cmp, (unsigned long long)v);
+}
+__device__ __forceinline__ uint32_t ldg_key(const uint32_t *p) { return __ldg(p); }
+__device__ __forceinline__ uint64_t ldg_key(const uint64_t *p) { return __ldg((const unsigned long long *)p); }
 
 }  // namespace
 
-// ROWS = rows per block (32 or 64: one or two mask words per slot), KPT = column keys per lane per trip (a column's
-// run of one range, fill / ROWS keys on average, should fit one trip)
-template <int SLOTS_LOG2, int THREADS, int CTAS, int ROWS, int KPT>
+// KT = key word of the sets (uint32_t low words, or the full uint64_t h of keys wider than 42 bits), ROWS = rows per
+// block (32 or 64: one or two mask words per slot), KPT = column keys per lane per trip (a column's run of one range,
+// fill / ROWS keys on average, should fit one trip)
+template <typename KT, int SLOTS_LOG2, int THREADS, int CTAS, int ROWS, int KPT>
 __global__ void __launch_bounds__(THREADS, CTAS)
     k_join(const SetDesc *__restrict__ sets, JoinPlan plan, uint32_t *__restrict__ counts,
            unsigned long long *__restrict__ work_counter, uint32_t *__restrict__ err) {
@@ -89,14 +113,16 @@ __global__ void __launch_bounds__(THREADS, CTAS)
     static_assert(ROWS == 32 || ROWS == 64, "one or two mask words per slot");
     static_assert(THREADS >= ROWS, "one thread per row looks the runs up");
     extern __shared__ __align__(16) uint32_t sm_tab[];
-    uint32_t *keys = sm_tab, *masks = sm_tab + SLOTS;  // masks: word w of slot s at masks[w * SLOTS + s]
+    constexpr uint32_t KS = (uint32_t)sizeof(KT);
+    KT *keys = (KT *)sm_tab;
+    uint32_t *masks = sm_tab + SLOTS * (KS / 4u);  // masks: word w of slot s at masks[w * SLOTS + s]
     // Everything a task needs before its table can be built, looked up by warp 0 WHILE the other warps still probe
     // the previous task's table (the look-ups are a chain of dependent global loads): double-buffered.
     struct TaskInfo {
         unsigned long long task;
         uint32_t level, rho, fill, min_id;
         uint32_t rowid[ROWS], rowpos[ROWS];
-        RangeRun run[ROWS];
+        RangeRun<KT> run[ROWS];
     };
     __shared__ TaskInfo s_ti[2];
     __shared__ uint32_t s_colgrp;
@@ -106,7 +132,7 @@ __global__ void __launch_bounds__(THREADS, CTAS)
     // from the generic pointer at every probe
     uint32_t kbase = (uint32_t)__cvta_generic_to_shared(keys);
     asm volatile("" : "+r"(kbase));
-    constexpr uint32_t M4 = SMASK << 2, MASKS_OFF = SLOTS * 4u;
+    constexpr uint32_t M4 = SMASK << 2, MASKS_OFF = SLOTS * KS;  // byte offset of mask word 0 behind the keys
 
     // warp 0: take the next task from the global counter and look up its rows and their runs
     auto prepare = [&](TaskInfo &ti) {
@@ -131,8 +157,8 @@ __global__ void __launch_bounds__(THREADS, CTAS)
             if (pos != JOIN_INVALID) id = plan.row_ids ? plan.row_ids[pos] : pos;
             ti.rowpos[r] = pos;
             ti.rowid[r] = id;
-            RangeRun rr{};
-            if (id != JOIN_INVALID) rr = range_run(sets[id].main, L, rho);
+            RangeRun<KT> rr{};
+            if (id != JOIN_INVALID) rr = range_run<KT>(sets[id].main, L, rho);
             ti.run[r] = rr;
             total += rr.hi - rr.lo;
             mn = min(mn, id);
@@ -153,15 +179,17 @@ __global__ void __launch_bounds__(THREADS, CTAS)
         const TaskInfo &ti = s_ti[p];
         if (ti.task >= plan.n_tasks) return;
         const uint32_t L = ti.level, rho = ti.rho;
-        const uint32_t fs = (uint32_t)plan.key_bits - L;  // 1..31: low-word bits below the range index
-        // no key of the range has this low word: bit 31 lies inside the range index and is flipped
-        const uint32_t EMPTY = ((uint32_t)((unsigned long long)rho << fs)) ^ 0x80000000u;
+        const uint32_t fs = (uint32_t)plan.key_bits - L;  // key bits below the range index (32-bit low words: 1..31)
+        // 32-bit low words: no key of the range has this low word (bit 31 lies inside the range index and is
+        // flipped); 64-bit keys: the all-ones word is never a key (KEY_SENTINEL)
+        const KT EMPTY = KS == 4 ? (KT)(((uint32_t)((unsigned long long)rho << fs)) ^ 0x80000000u) : (KT)~(KT)0;
         const bool overfull = ti.fill > MAXFILL;
         if (overfull && tid == 0) atomicExch(err, 1u);  // the host redoes the call with the merge kernel
         {  // clear the table
             uint4 *k4 = (uint4 *)keys, *m4 = (uint4 *)masks;
-            const uint4 e4 = make_uint4(EMPTY, EMPTY, EMPTY, EMPTY), z4 = make_uint4(0, 0, 0, 0);
-            for (uint32_t i = tid; i < SLOTS / 4; i += THREADS) k4[i] = e4;
+            const uint32_t e_lo = (uint32_t)EMPTY, e_hi = KS == 4 ? (uint32_t)EMPTY : 0xFFFFFFFFu;
+            const uint4 e4 = make_uint4(e_lo, e_hi, e_lo, e_hi), z4 = make_uint4(0, 0, 0, 0);
+            for (uint32_t i = tid; i < SLOTS * KS / 16; i += THREADS) k4[i] = e4;
             for (uint32_t i = tid; i < RW * SLOTS / 4; i += THREADS) m4[i] = z4;
         }
         if (tid == 0) s_colgrp = 0;
@@ -171,23 +199,23 @@ __global__ void __launch_bounds__(THREADS, CTAS)
         // a warp per row; the keys of a row are requested KB per lane at a time before any is inserted
         constexpr int KB = 192 / ROWS;  // a row's run is ~fill / ROWS keys: one batch
         for (uint32_t r = warp; r < (uint32_t)ROWS && !overfull; r += NW) {
-            const RangeRun rr = ti.run[r];
+            const RangeRun<KT> rr = ti.run[r];
             const uint32_t bit = 1u << (r & 31u);
             uint32_t *mw = masks + (r >> 5) * SLOTS;
             for (uint32_t base = rr.lo; base < rr.hi; base += 32u * KB) {
-                uint32_t kk[KB];
+                KT kk[KB];
 #pragma unroll
                 for (int q = 0; q < KB; q++) {
                     const uint32_t i = base + q * 32u + lane;
-                    kk[q] = i < rr.hi ? __ldg(rr.lows + i) : 0u;
+                    kk[q] = i < rr.hi ? ldg_key(rr.lows + i) : (KT)0;
                 }
 #pragma unroll
                 for (int q = 0; q < KB; q++) {
                     const uint32_t i = base + q * 32u + lane;
                     if (i >= rr.hi || ((kk[q] >> fs) & rr.fm) != rr.fv) continue;
-                    uint32_t s = join_hash<SLOTS_LOG2>(kk[q]);
+                    uint32_t s = join_off4<SLOTS_LOG2>(kk[q]) >> 2;
                     for (;;) {
-                        const uint32_t old = atomicCAS(&keys[s], EMPTY, kk[q]);
+                        const KT old = cas_key(&keys[s], EMPTY, kk[q]);
                         if (old == EMPTY || old == kk[q]) {
                             atomicOr(&mw[s], bit);
                             break;
@@ -226,22 +254,23 @@ __global__ void __launch_bounds__(THREADS, CTAS)
             if (g >= G) break;
             const uint32_t c_mine = cbeg + g + lane * G;
             uint32_t col_id = 0;
-            RangeRun cr{};
+            RangeRun<KT> cr{};
             if (c_mine < cend) {
                 col_id = plan.col_ids ? plan.col_ids[c_mine] : c_mine;
-                cr = range_run(sets[col_id].main, L, rho);
+                cr = range_run<KT>(sets[col_id].main, L, rho);
             }
             const uint32_t nb = (ncols - g + G - 1u) / G;  // columns of this group (<= 32)
-            uint32_t nk[KPT], nlo, nhi;
-            const uint32_t *nlows;
+            KT nk[KPT];
+            uint32_t nlo, nhi;
+            const KT *nlows;
             auto fetch = [&](uint32_t j) {
                 nlo = __shfl_sync(FULL, cr.lo, j);
                 nhi = __shfl_sync(FULL, cr.hi, j);
-                nlows = (const uint32_t *)__shfl_sync(FULL, (unsigned long long)cr.lows, j);
+                nlows = (const KT *)__shfl_sync(FULL, (unsigned long long)cr.lows, j);
 #pragma unroll
                 for (int q = 0; q < KPT; q++) {
                     const uint32_t i = nlo + q * 32u + lane;
-                    nk[q] = i < nhi ? __ldg(nlows + i) : 0u;
+                    nk[q] = i < nhi ? ldg_key(nlows + i) : (KT)0;
                 }
             };
             fetch(0);
@@ -254,13 +283,13 @@ __global__ void __launch_bounds__(THREADS, CTAS)
                 for (int x = 0; x < 8; x++) acc[w][x] = 0;
             for (uint32_t j = 0; j < nb; j++) {
                 const uint32_t lo = nlo, hi = nhi;
-                const uint32_t *lows = nlows;
-                uint32_t k[KPT];
+                const KT *lows = nlows;
+                KT k[KPT];
 #pragma unroll
                 for (int q = 0; q < KPT; q++) k[q] = nk[q];
                 if (j + 1 < nb) fetch(j + 1);
                 if (lo >= hi) continue;
-                const uint32_t fm = __shfl_sync(FULL, cr.fm, j), fv = __shfl_sync(FULL, cr.fv, j);
+                const KT fm = __shfl_sync(FULL, cr.fm, j), fv = __shfl_sync(FULL, cr.fv, j);
                 const uint32_t cid = __shfl_sync(FULL, col_id, j);
                 // rows that form a requested pair with this column (upper triangle: row id < column id)
                 uint32_t rowmask[RW];
@@ -290,21 +319,21 @@ __global__ void __launch_bounds__(THREADS, CTAS)
 #pragma unroll
                     for (int q = 0; q < KPT; q++) {
                         const uint32_t i = base + q * 32u + lane;
-                        if (base != lo) k[q] = i < hi ? __ldg(lows + i) : 0u;
+                        if (base != lo) k[q] = i < hi ? ldg_key(lows + i) : (KT)0;
                         const bool ok = i < hi && ((k[q] >> fs) & fm) == fv;
                         // every lane loads (lanes without a key probe slot hash(0), a broadcast) so the probe is
                         // branch-free; an empty slot carries mask 0, so a stray hit on it counts nothing
-                        uint32_t off = ((k[q] * 0x9E3779B1u) >> (30 - SLOTS_LOG2)) & M4;
-                        uint32_t e = lds_u32(kbase + off);
+                        uint32_t off = join_off4<SLOTS_LOG2>(k[q]);
+                        KT e = lds_key(kbase, off, k[q]);
                         e = ok ? e : EMPTY;
                         while (e != k[q] && e != EMPTY) {
                             off = (off + 4u) & M4;
-                            e = lds_u32(kbase + off);
+                            e = lds_key(kbase, off, k[q]);
                         }
                         const bool hit = ok && e == k[q];
 #pragma unroll
                         for (int w = 0; w < RW; w++) {
-                            const uint32_t mv = lds_u32(kbase + off + MASKS_OFF * (1u + w));
+                            const uint32_t mv = lds_u32(kbase + off + MASKS_OFF + w * (SLOTS * 4u));
                             m[w][q] = hit ? (mv & rowmask[w]) : 0u;
                             anym |= m[w][q];
                         }
@@ -340,23 +369,26 @@ __global__ void __launch_bounds__(THREADS, CTAS)
     }
 }
 
-// Geometries: <log2 slots, threads per CTA, CTAs per SM, rows per block, keys per lane per trip>; a slot is a
-// 4-byte key plus one 4-byte mask word per 32 rows
-#define GKD_FOR_EACH_JCFG(X)                                                                                   \
+// Geometries: <log2 slots, threads per CTA, CTAs per SM, rows per block, keys per lane per trip>; a slot is a key
+// word plus one 4-byte mask word per 32 rows.  The first N_JCFG32 entries serve 32-bit low words, the rest 64-bit keys.
+#define GKD_FOR_EACH_JCFG32(X)                                                                                   \
     X(0, 14, 1024, 1, 64, 3) X(1, 14, 1024, 1, 32, 6) X(2, 13, 512, 2, 32, 3) X(3, 14, 512, 1, 64, 3) X(4, 13, 512, 2, 64, 2) \
     X(5, 12, 256, 4, 32, 2) X(6, 14, 1024, 1, 64, 4) X(7, 14, 768, 1, 64, 3)
-constexpr int N_JCFG = 8;
-static const int g_jcfg_slots_log2[N_JCFG] = {14, 14, 13, 14, 13, 12, 14, 14};
-static const int g_jcfg_rows[N_JCFG] = {64, 32, 32, 64, 64, 32, 64, 64};
+#define GKD_FOR_EACH_JCFG64(X) X(8, 13, 768, 1, 64, 2) X(9, 13, 512, 2, 32, 3) X(10, 13, 1024, 1, 64, 2) X(11, 12, 512, 2, 64, 1)
+constexpr int N_JCFG32 = 8, N_JCFG = 12;
+static const int g_jcfg_slots_log2[N_JCFG] = {14, 14, 13, 14, 13, 12, 14, 14, 13, 13, 13, 12};
+static const int g_jcfg_rows[N_JCFG] = {64, 32, 32, 64, 64, 32, 64, 64, 64, 32, 64, 64};
 
-// GKD_JOIN_CFG pins a geometry; otherwise 64-row blocks when the call has enough rows and columns to fill them
-// (measured on the B200: 64 rows win from ~500 columns on, 32 rows below), 32-row blocks else
-int join_pick_cfg(uint32_t n_rows, uint32_t n_cols) {
+// GKD_JOIN_CFG pins a geometry (of the right key width); otherwise 64-row blocks when the call has enough rows and
+// columns to fill them (measured on the B200: 64 rows win from ~500 columns on, 32 rows below), 32-row blocks else
+int join_pick_cfg(uint32_t n_rows, uint32_t n_cols, int low_bits) {
+    const int first = low_bits == 32 ? 0 : N_JCFG32, last = low_bits == 32 ? N_JCFG32 : N_JCFG;
     if (const char *e = getenv("GKD_JOIN_CFG")) {
         const int c = atoi(e);
-        if (c >= 0 && c < N_JCFG) return c;
+        if (c >= first && c < last) return c;
     }
-    return (n_rows >= 192 && n_cols >= 448) ? 7 : 1;
+    const bool big = n_rows >= 192 && n_cols >= 448;
+    return low_bits == 32 ? (big ? 7 : 1) : (big ? 8 : 9);
 }
 uint32_t join_cfg_slots(int cfg) { return 1u << g_jcfg_slots_log2[cfg]; }
 uint32_t join_cfg_rows(int cfg) { return (uint32_t)g_jcfg_rows[cfg]; }
@@ -364,10 +396,16 @@ uint32_t join_cfg_rows(int cfg) { return (uint32_t)g_jcfg_rows[cfg]; }
 cudaError_t join_configure() {
     cudaError_t e;
 #define X(i, SL, T, C, R, K)                                                                                   \
-    if ((e = cudaFuncSetAttribute(k_join<SL, T, C, R, K>, cudaFuncAttributeMaxDynamicSharedMemorySize,        \
+    if ((e = cudaFuncSetAttribute(k_join<uint32_t, SL, T, C, R, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                   (4 << SL) * (1 + R / 32))) != cudaSuccess)                                   \
         return e;
-    GKD_FOR_EACH_JCFG(X)
+    GKD_FOR_EACH_JCFG32(X)
+#undef X
+#define X(i, SL, T, C, R, K)                                                                                   \
+    if ((e = cudaFuncSetAttribute(k_join<uint64_t, SL, T, C, R, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                  (4 << SL) * (2 + R / 32))) != cudaSuccess)                                   \
+        return e;
+    GKD_FOR_EACH_JCFG64(X)
 #undef X
     return cudaSuccess;
 }
@@ -378,15 +416,20 @@ cudaError_t launch_join(const SetDesc *sets, const JoinPlan &plan, uint32_t *cou
     cudaError_t e = cudaMemsetAsync(work_counter, 0, sizeof(unsigned long long), s);
     if (e != cudaSuccess) return e;
     const int c = plan.cfg;
-#define X(i, SL, T, C, R, K)                                                                                    \
+#define LAUNCH(KT, KW, i, SL, T, C, R, K)                                                                       \
     if (c == i) {                                                                                               \
         unsigned long long grid = (unsigned long long)n_sms * C;                                                \
         if (grid > plan.n_tasks) grid = plan.n_tasks;                                                           \
-        k_join<SL, T, C, R, K><<<(unsigned)grid, T, (4 << SL) * (1 + R / 32), s>>>(sets, plan, counts, work_counter, err); \
+        k_join<KT, SL, T, C, R, K><<<(unsigned)grid, T, (4 << SL) * (KW + R / 32), s>>>(sets, plan, counts, work_counter, err); \
         return cudaGetLastError();                                                                              \
     }
-    GKD_FOR_EACH_JCFG(X)
+#define X(i, SL, T, C, R, K) LAUNCH(uint32_t, 1, i, SL, T, C, R, K)
+    GKD_FOR_EACH_JCFG32(X)
 #undef X
+#define X(i, SL, T, C, R, K) LAUNCH(uint64_t, 2, i, SL, T, C, R, K)
+    GKD_FOR_EACH_JCFG64(X)
+#undef X
+#undef LAUNCH
     return cudaErrorInvalidValue;
 }
 

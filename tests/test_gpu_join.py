@@ -2,7 +2,7 @@
 
 GKD_ISECT_ALGO (read when a context is created) pins the kernel-4 variant: "merge" = bucket merge only,
 "join" = block join for every call it structurally serves (upper-triangle ranges and query x reference
-rectangles on 32-bit low words), default = chosen per call.  Both must give the same exact counts, and the same
+rectangles; 32-bit low words and 64-bit keys have their own table layouts), default = chosen per call.  Both must give the same exact counts, and the same
 doubles, as the oracle's sorted-integer restatement of SequenceKmers.similarity / distance.
 """
 import numpy as np
@@ -51,7 +51,8 @@ LENS = ([300_000] * 20 + [310_000, 150_000, 290_000, 25, 600_000, 40_000, 1_200_
         + [280_000] * 23 + [2_100_000, 20, 75_000])
 
 
-@pytest.mark.parametrize("k,alphabet", [(21, gkd.DNA), (16, gkd.DNA), (12, gkd.DNA), (5, gkd.PROT)])
+@pytest.mark.parametrize("k,alphabet", [(21, gkd.DNA), (16, gkd.DNA), (12, gkd.DNA), (5, gkd.PROT), (25, gkd.DNA), (32, gkd.DNA),
+                                        (8, gkd.PROT)])
 def test_block_join_matches_merge_and_oracle(orc, k, alphabet, monkeypatch):
     """56 sets of mixed sizes (25 bp ... 2.1 Mbp, one empty, related families and unrelated ones): the whole
     triangle, ranges that start and end inside rows, and rectangles with few and many query rows (the kernel
@@ -85,14 +86,17 @@ def test_block_join_matches_merge_and_oracle(orc, k, alphabet, monkeypatch):
                 t += 1
 
 
-@pytest.mark.parametrize("jcfg,fill", [(0, None), (1, None), (2, None), (3, None), (4, None), (5, None), (6, None), (7, None), (1, 45), (4, 5)])
-def test_every_join_configuration_is_exact(jcfg, fill, monkeypatch):
-    """GKD_JOIN_CFG pins the table geometry, GKD_JOIN_FILL the target load: every geometry gives the merge
-    kernel's counts, for sets whose own bucket tables are finer and coarser than the key ranges."""
+@pytest.mark.parametrize("k,jcfg,fill", [(21, 0, None), (21, 1, None), (21, 2, None), (21, 3, None), (21, 4, None), (21, 5, None),
+                                         (21, 6, None), (21, 7, None), (21, 1, 45), (21, 5, 5),
+                                         (25, 8, None), (25, 9, None), (25, 10, None), (25, 11, None), (25, 9, 45)])
+def test_every_join_configuration_is_exact(k, jcfg, fill, monkeypatch):
+    """GKD_JOIN_CFG pins the table geometry (0-7: 32-bit low words, 8-11: 64-bit keys), GKD_JOIN_FILL the target
+    load: every geometry gives the merge kernel's counts, for sets whose own bucket tables are finer and coarser
+    than the key ranges."""
     seqs = _seqs(5, [200_000] * 34 + [1_500_000, 30_000, 2_000, 800_000], families=2)
     calls = [("all", ()), ("rect", (list(range(2, 38)), list(range(0, 36))))]
-    merge, _ = _run(monkeypatch, "merge", 21, gkd.DNA, seqs, calls)
-    join, kj = _run(monkeypatch, "join", 21, gkd.DNA, seqs, calls, jcfg=jcfg, fill=fill)
+    merge, _ = _run(monkeypatch, "merge", k, gkd.DNA, seqs, calls)
+    join, kj = _run(monkeypatch, "join", k, gkd.DNA, seqs, calls, jcfg=jcfg, fill=fill)
     assert kj == [5, 5]
     for (mi, md), (ji, jd) in zip(merge, join):
         assert np.array_equal(mi, ji) and np.array_equal(md, jd)
