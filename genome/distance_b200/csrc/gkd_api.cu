@@ -37,7 +37,8 @@ thread_local std::string g_create_error;
 
 constexpr uint64_t PACK_SLAB_BYTES = 256ull << 20;
 constexpr uint64_t STAGE_BYTES = 32ull << 20;  // text staged per piece (multiple of 32 positions)
-constexpr int N_STAGE = 3;
+constexpr int N_STAGE = 3;    // pinned bounce buffers (pageable input)
+constexpr int N_DSTAGE = 8;   // device staging buffers: the copies may run this many pieces ahead of kernel 1
 constexpr uint64_t DEFAULT_WORKSPACE = 8ull << 30;
 constexpr uint64_t PAIR_CHUNK = 64ull << 20;  // pairs per distance launch
 constexpr uint64_t SET_BLOCK_ALIGN = 256;     // every set block of an arena starts on this boundary
@@ -53,6 +54,7 @@ struct GenomeRec {
     uint64_t n_pos = 0;         // stream positions (residues + separators)
     void *d_codes = nullptr;    // packed stream (slab memory)
     uint32_t *d_mask = nullptr;
+    cudaEvent_t ready = nullptr;  // recorded on the ingest stream behind this genome's copy + pack (nullptr: nothing pending)
     bool built = false;
     SetDesc desc{{nullptr, nullptr, 0, 0}, {nullptr, nullptr, 0, 0}};
     gkd_packed_set packed{};    // layout relative to the base of `arena`
@@ -94,6 +96,12 @@ struct gkd_ctx {
     uint32_t table_tmax = 16, isect_tmax = 16;
     MixParams mix{};
     cudaStream_t stream = nullptr;
+    // ingest (host->device copies of the text + kernel 1) runs on its own two streams, so the copies of later genomes
+    // overlap the set construction of earlier build batches; a batch waits for the `ready` event of its last genome
+    cudaStream_t copy_stream = nullptr;  // the copies of the text into the staging buffers
+    cudaStream_t pack_stream = nullptr;  // kernel 1 (staging buffer -> packed stream in the slab), behind each copy
+    cudaEvent_t slab_ev = nullptr;
+    std::vector<cudaEvent_t> ev_pool;
     bool poisoned = false;
     std::string err;
 
@@ -106,8 +114,10 @@ struct gkd_ctx {
 
     char *bounce[N_STAGE] = {nullptr, nullptr, nullptr};
     cudaEvent_t bounce_ev[N_STAGE] = {nullptr, nullptr, nullptr};
-    char *stage_dev[N_STAGE] = {nullptr, nullptr, nullptr};
-    int stage_next = 0;
+    char *stage_dev[N_DSTAGE] = {};
+    cudaEvent_t copied[N_DSTAGE] = {}, packed[N_DSTAGE] = {};  // staging buffer s: text has landed / kernel 1 has consumed it
+    bool packed_valid[N_DSTAGE] = {};
+    int stage_next = 0, dstage_next = 0;
 
     DevBuf keys_a, keys_b, tile_hist, tile_uniq, genome_counts, batch_genomes, set_build;
     DevBuf d_sets, counts, pal_counts, d_inter, d_dist, d_ca, d_cb, ids_a, ids_b, work_counter;
@@ -186,6 +196,9 @@ int slab_alloc(gkd_ctx *c, uint64_t bytes, void **out) {
     s.used = bytes;
     void *p = nullptr;
     CK(cudaMallocAsync(&p, s.size, c->stream));
+    // the ingest stream writes the slab: order it behind the allocation
+    CK(cudaEventRecord(c->slab_ev, c->stream));
+    CK(cudaStreamWaitEvent(c->pack_stream, c->slab_ev, 0));
     s.base = (char *)p;
     c->slabs.push_back(s);
     *out = s.base;
@@ -346,12 +359,16 @@ int add_genome(gkd_ctx *c, const std::vector<Part> &parts, const std::string &la
     do {
         const uint64_t q1 = std::min<uint64_t>(n_pos, q0 + STAGE_BYTES);
         const uint64_t plen = q1 - q0;
-        const int s = c->stage_next;
-        c->stage_next = (c->stage_next + 1) % N_STAGE;
+        const int s = c->dstage_next;
+        c->dstage_next = (c->dstage_next + 1) % N_DSTAGE;
         char *dev = c->stage_dev[s];
+        // the staging buffer is free again once kernel 1 has consumed its previous piece
+        if (c->packed_valid[s]) CK(cudaStreamWaitEvent(c->copy_stream, c->packed[s], 0));
         if (kind == MEM_PAGEABLE) {
-            CK(cudaEventSynchronize(c->bounce_ev[s]));
-            char *dst = c->bounce[s];
+            const int bs = c->stage_next;
+            c->stage_next = (c->stage_next + 1) % N_STAGE;
+            CK(cudaEventSynchronize(c->bounce_ev[bs]));
+            char *dst = c->bounce[bs];
             uint64_t w = 0;
             while (w < plen) {
                 if (pending_sep) {
@@ -370,13 +387,13 @@ int add_genome(gkd_ctx *c, const std::vector<Part> &parts, const std::string &la
                     if (pi < parts.size() && parts[pi].new_contig) pending_sep = true;
                 }
             }
-            if (plen) CK(cudaMemcpyAsync(dev, dst, plen, cudaMemcpyHostToDevice, c->stream));
-            CK(cudaEventRecord(c->bounce_ev[s], c->stream));
+            if (plen) CK(cudaMemcpyAsync(dev, dst, plen, cudaMemcpyHostToDevice, c->copy_stream));
+            CK(cudaEventRecord(c->bounce_ev[bs], c->copy_stream));
             c->m.h2d_bytes += plen;
         } else {
             // pinned host or device memory: copy each run straight into the staged text; the
             // separators are the zero fill
-            if (plen) CK(cudaMemsetAsync(dev, STREAM_SEPARATOR, plen, c->stream));
+            if (plen) CK(cudaMemsetAsync(dev, STREAM_SEPARATOR, plen, c->copy_stream));
             uint64_t w = 0;
             while (w < plen) {
                 if (pending_sep) {
@@ -386,7 +403,7 @@ int add_genome(gkd_ctx *c, const std::vector<Part> &parts, const std::string &la
                 }
                 const Part &p = parts[pi];
                 uint64_t take = std::min<uint64_t>(p.len - pofs, plen - w);
-                if (take) CK(cudaMemcpyAsync(dev + w, p.ptr + pofs, take, cudaMemcpyDefault, c->stream));
+                if (take) CK(cudaMemcpyAsync(dev + w, p.ptr + pofs, take, cudaMemcpyDefault, c->copy_stream));
                 w += take;
                 pofs += take;
                 if (pofs == p.len) {
@@ -397,18 +414,31 @@ int add_genome(gkd_ctx *c, const std::vector<Part> &parts, const std::string &la
             }
             if (kind == MEM_PINNED) c->m.h2d_bytes += plen;
         }
-        // kernel 1 on this piece (q0 is a multiple of 32 positions)
+        // kernel 1 on this piece (q0 is a multiple of 32 positions), on its own stream behind the copy: the next
+        // copies do not wait for it
+        CK(cudaEventRecord(c->copied[s], c->copy_stream));
+        CK(cudaStreamWaitEvent(c->pack_stream, c->copied[s], 0));
         if (prot)
-            CK(launch_pack_prot(dev, plen, (uint8_t *)codes + q0, (uint32_t *)mask + q0 / 32, c->stream));
+            CK(launch_pack_prot(dev, plen, (uint8_t *)codes + q0, (uint32_t *)mask + q0 / 32, c->pack_stream));
         else
             CK(launch_pack_dna(dev, plen, (uint64_t *)codes + q0 / 32, (uint32_t *)mask + q0 / 32,
-                               c->cfg.alphabet == GKD_RNA, c->stream));
+                               c->cfg.alphabet == GKD_RNA, c->pack_stream));
+        CK(cudaEventRecord(c->packed[s], c->pack_stream));
+        c->packed_valid[s] = true;
         c->m.launches++;
         q0 = q1;
     } while (q0 < n_pos);
     // contract (gkd.h): pageable text was copied into the bounce buffers before this returns; pinned and
     // device text is read by the stream-ordered copies above and must stay valid until gkd_build_sets
-    // (which synchronises) -- no per-genome synchronisation here.
+    // (which waits for them and synchronises) -- no per-genome synchronisation here.
+    if (c->ev_pool.empty()) {
+        cudaEvent_t e = nullptr;
+        CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        c->ev_pool.push_back(e);
+    }
+    g.ready = c->ev_pool.back();
+    c->ev_pool.pop_back();
+    CK(cudaEventRecord(g.ready, c->pack_stream));
     c->m.residues_packed += n_pos;
     if (out_id) *out_id = (uint32_t)c->genomes.size();
     c->genomes.push_back(std::move(g));
@@ -705,6 +735,12 @@ int build_batch(gkd_ctx *c, uint32_t first, uint32_t last) {
         ids.push_back(id);
         c->m.kmer_positions += b.n_slots;
     }
+    // the packed streams of this batch come from the ingest stream (in order: the last pending event covers all)
+    for (uint32_t id = last; id-- > first;)
+        if (c->genomes[id].ready) {
+            CK(cudaStreamWaitEvent(c->stream, c->genomes[id].ready, 0));
+            break;
+        }
     SortPlan plan{};
     int rc = plan_batch(c, bg, plan, std::max<uint64_t>(raw, 16), tiles);
     if (rc) return rc;
@@ -1216,6 +1252,15 @@ int gkd_create(gkd_ctx **out, const gkd_config *cfg) {
     } while (0)
     CK_CREATE(cudaSetDevice(cfg->device));
     CK_CREATE(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    {
+        // highest priority: the pack kernels are tiny and sit between the copies, so they must not queue behind the
+        // grids of a running build batch (the next copy of the stream could not start)
+        int prio_lo = 0, prio_hi = 0;
+        CK_CREATE(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+        CK_CREATE(cudaStreamCreateWithPriority(&c->copy_stream, cudaStreamNonBlocking, prio_hi));
+        CK_CREATE(cudaStreamCreateWithPriority(&c->pack_stream, cudaStreamNonBlocking, prio_hi));
+    }
+    CK_CREATE(cudaEventCreateWithFlags(&c->slab_ev, cudaEventDisableTiming));
     cudaMemPool_t pool;
     CK_CREATE(cudaDeviceGetDefaultMemPool(&pool, cfg->device));
     uint64_t thresh = UINT64_MAX;
@@ -1223,7 +1268,11 @@ int gkd_create(gkd_ctx **out, const gkd_config *cfg) {
     for (int i = 0; i < N_STAGE; i++) {
         CK_CREATE(cudaMallocHost((void **)&c->bounce[i], STAGE_BYTES));
         CK_CREATE(cudaEventCreateWithFlags(&c->bounce_ev[i], cudaEventDisableTiming));
+    }
+    for (int i = 0; i < N_DSTAGE; i++) {
         CK_CREATE(cudaMalloc((void **)&c->stage_dev[i], STAGE_BYTES + 256));
+        CK_CREATE(cudaEventCreateWithFlags(&c->copied[i], cudaEventDisableTiming));
+        CK_CREATE(cudaEventCreateWithFlags(&c->packed[i], cudaEventDisableTiming));
     }
     for (auto &ev : c->ev) CK_CREATE(cudaEventCreate(&ev));
     // function attributes are per device: every context sets them for its own device
@@ -1257,10 +1306,22 @@ static int trim_free_arenas(gkd_ctx *c, size_t keep) {
     return GKD_OK;
 }
 
+// the `ready` events of genomes first.. go back to the pool (both streams are idle when this is called)
+static void recycle_events(gkd_ctx *c, size_t first) {
+    for (size_t i = first; i < c->genomes.size(); i++)
+        if (c->genomes[i].ready) {
+            c->ev_pool.push_back(c->genomes[i].ready);
+            c->genomes[i].ready = nullptr;
+        }
+}
+
 int gkd_reset(gkd_ctx *c) {
     CHECK_CTX(c);
     CK(cudaSetDevice(c->cfg.device));
+    CK(cudaStreamSynchronize(c->copy_stream));
+    CK(cudaStreamSynchronize(c->pack_stream));
     CK(cudaStreamSynchronize(c->stream));
+    recycle_events(c, 0);
     release_arenas_from(c, 0);
     int rc = trim_free_arenas(c, 16);
     if (rc) return rc;
@@ -1280,7 +1341,10 @@ int gkd_truncate(gkd_ctx *c, uint32_t n_keep) {
     CHECK_CTX(c);
     if (n_keep >= c->genomes.size()) return GKD_OK;
     CK(cudaSetDevice(c->cfg.device));
+    CK(cudaStreamSynchronize(c->copy_stream));
+    CK(cudaStreamSynchronize(c->pack_stream));
     CK(cudaStreamSynchronize(c->stream));
+    recycle_events(c, n_keep);
     // arenas are created in id order, one per build/import/adopt batch: recycle those that hold only dropped sets
     size_t keep = c->arenas.size();
     while (keep > 0 && c->arenas[keep - 1].first_id >= n_keep) keep--;
@@ -1296,7 +1360,12 @@ int gkd_truncate(gkd_ctx *c, uint32_t n_keep) {
 int gkd_destroy(gkd_ctx *c) {
     if (!c) return GKD_EINVAL;
     cudaSetDevice(c->cfg.device);
+    if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
+    if (c->pack_stream) cudaStreamSynchronize(c->pack_stream);
     cudaStreamSynchronize(c->stream);
+    recycle_events(c, 0);
+    for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
+    if (c->slab_ev) cudaEventDestroy(c->slab_ev);
     for (auto &a : c->arenas)
         if (a.owned) cudaFreeAsync(a.base, c->stream);
     for (auto &a : c->free_arenas) cudaFreeAsync(a.first, c->stream);
@@ -1312,10 +1381,16 @@ int gkd_destroy(gkd_ctx *c) {
     for (int i = 0; i < N_STAGE; i++) {
         if (c->bounce[i]) cudaFreeHost(c->bounce[i]);
         if (c->bounce_ev[i]) cudaEventDestroy(c->bounce_ev[i]);
+    }
+    for (int i = 0; i < N_DSTAGE; i++) {
         if (c->stage_dev[i]) cudaFree(c->stage_dev[i]);
+        if (c->copied[i]) cudaEventDestroy(c->copied[i]);
+        if (c->packed[i]) cudaEventDestroy(c->packed[i]);
     }
     for (auto &ev : c->ev)
         if (ev) cudaEventDestroy(ev);
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+    if (c->pack_stream) cudaStreamDestroy(c->pack_stream);
     if (c->stream) cudaStreamDestroy(c->stream);
     cudaGetLastError();
     delete c;
