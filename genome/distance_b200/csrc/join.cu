@@ -380,14 +380,15 @@ static const int g_jcfg_slots_log2[N_JCFG] = {14, 14, 13, 14, 13, 12, 14, 14, 13
 static const int g_jcfg_rows[N_JCFG] = {64, 32, 32, 64, 64, 32, 64, 64, 64, 32, 64, 64};
 
 // GKD_JOIN_CFG pins a geometry (of the right key width); otherwise 64-row blocks when the call has enough rows and
-// columns to fill them (measured on the B200: 64 rows win from ~500 columns on, 32 rows below), 32-row blocks else
+// columns to fill them (measured on the B200, tools/bench_rect.py: 125 x 375 and 300 x 300 blocks are 4-7 % faster
+// with 64 rows), 32-row blocks for smaller calls
 int join_pick_cfg(uint32_t n_rows, uint32_t n_cols, int low_bits) {
     const int first = low_bits == 32 ? 0 : N_JCFG32, last = low_bits == 32 ? N_JCFG32 : N_JCFG;
     if (const char *e = getenv("GKD_JOIN_CFG")) {
         const int c = atoi(e);
         if (c >= first && c < last) return c;
     }
-    const bool big = n_rows >= 192 && n_cols >= 448;
+    const bool big = n_rows >= 96 && n_cols >= 128;
     return low_bits == 32 ? (big ? 7 : 1) : (big ? 8 : 9);
 }
 uint32_t join_cfg_slots(int cfg) { return 1u << g_jcfg_slots_log2[cfg]; }
