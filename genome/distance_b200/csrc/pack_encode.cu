@@ -202,6 +202,32 @@ __global__ void __launch_bounds__(ENC_THREADS)
         dst[idx] = stage[(idx / ENC_PER_THREAD) * ENC_STRIDE + (idx % ENC_PER_THREAD)];
 }
 
+// One global atomic per (tile, bin) reserves the tile's room in every bin; s_bin[b] turns from the tile's key count
+// into its offset in bin b (0xFFFFFFFF: the bin would overflow).  A thread owns up to four bins per round and
+// issues their atomics back to back, so their latencies overlap instead of adding up.
+__device__ __forceinline__ void reserve_bins(uint32_t *s_bin, uint32_t n_bins, uint32_t *__restrict__ cursor, uint32_t cap,
+                                             uint32_t *__restrict__ overflow) {
+    for (uint32_t b0 = threadIdx.x; b0 < n_bins; b0 += 4u * ENC_THREADS) {
+        uint32_t v[4], base[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const uint32_t b = b0 + u * ENC_THREADS;
+            v[u] = b < n_bins ? s_bin[b] : 0u;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) base[u] = v[u] ? atomicAdd(&cursor[b0 + u * ENC_THREADS], v[u]) : 0u;
+#pragma unroll
+        for (int u = 0; u < 4; u++)
+            if (v[u]) {
+                if (base[u] + v[u] > cap) {
+                    atomicExch(overflow, 1u);
+                    base[u] = 0xFFFFFFFFu;
+                }
+                s_bin[b0 + u * ENC_THREADS] = base[u];
+            }
+    }
+}
+
 // ---- kernel 2 fused with the MSD partition of kernel 3 (sort_msd.cu) --------------------------------------
 // The mixed keys are uniform, so a genome's bins (top p bits of h) have predictable sizes and get FIXED
 // capacity regions: no histogram pass, no scan.  The keys stay in registers; a tile ranks them by bin with
@@ -234,17 +260,7 @@ __global__ void __launch_bounds__(ENC_THREADS, 4)
             if (h != KEY_SENTINEL) rank[j] = atomicAdd(&s_bin[M.p ? (uint32_t)(h >> shift) : 0u], 1u);
         });
     __syncthreads();
-    for (uint32_t b = threadIdx.x; b < n_bins; b += ENC_THREADS) {
-        const uint32_t v = s_bin[b];
-        if (v) {
-            uint32_t base = atomicAdd(&bin_cursor[M.bin_first + b], v);
-            if (base + v > M.cap) {
-                atomicExch(overflow, 1u);
-                base = 0xFFFFFFFFu;
-            }
-            s_bin[b] = base;
-        }
-    }
+    reserve_bins(s_bin, n_bins, bin_cursor + M.bin_first, M.cap, overflow);
     __syncthreads();
     uint64_t *out = bins_out + M.bins_off;
 #pragma unroll
@@ -284,17 +300,7 @@ __global__ void __launch_bounds__(ENC_THREADS)
         if (key[j] != KEY_SENTINEL) rank[j] = atomicAdd(&s_bin[M.p ? (uint32_t)(key[j] >> shift) : 0u], 1u);
     }
     __syncthreads();
-    for (uint32_t b = threadIdx.x; b < n_bins; b += ENC_THREADS) {
-        const uint32_t v = s_bin[b];
-        if (v) {
-            uint32_t base = atomicAdd(&bin_cursor[M.bin_first + b], v);
-            if (base + v > M.cap) {
-                atomicExch(overflow, 1u);
-                base = 0xFFFFFFFFu;
-            }
-            s_bin[b] = base;
-        }
-    }
+    reserve_bins(s_bin, n_bins, bin_cursor + M.bin_first, M.cap, overflow);
     __syncthreads();
     uint64_t *out = bins_out + M.bins_off;
 #pragma unroll
