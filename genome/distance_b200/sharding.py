@@ -138,9 +138,8 @@ def ring_all_vs_all(eng, n_genomes: int, world: int, rank: int, device, panel_ge
     Panels are the unit of TRANSFER; the unit of COMPUTE is a group of consecutive panels that meet the same
     rows, up to `group_sets` sets (they may come from several peers): kernel 4's block join builds one table
     per (64 rows, key range) and probes every column of the call with it, so a call with many columns
-    amortises the tables.  The first group is a single panel (the compute can start as soon as it is there); the
-    transfers of group g+1 are in flight while group g is computed, so at most two groups of received sets are
-    resident beside the rank's own slice."""
+    amortises the tables.  The transfers of group g+1 are in flight while group g is computed, so at most
+    two groups of received sets are resident beside the rank's own slice."""
     import time
 
     import torch
@@ -206,14 +205,11 @@ def ring_all_vs_all(eng, n_genomes: int, world: int, rank: int, device, panel_ge
             torch.cuda.current_stream().synchronize()  # only what this stream waits for: the slot's transfer
         t_wait += time.perf_counter() - t0
 
-    # compute groups: consecutive slots with the same rows, at most group_sets received sets together.  The FIRST
-    # group is a single panel: its transfer only has the (short) diagonal block to hide behind, so the compute
-    # should start as soon as one panel is there; the bigger groups behind it arrive under its kernels.
+    # compute groups: consecutive slots with the same rows, at most group_sets received sets together
     groups, cur_g, cur_cols = [], [], 0
     for idx, slot in enumerate(slots):
         n_recv = slot[2]["count"] if slot[2] is not None else 0
-        cap = max(1, group_sets) if groups else min(max(1, group_sets), max(1, panel_genomes))
-        if cur_g and (slots[cur_g[0]][4] != slot[4] or cur_cols + n_recv > cap):
+        if cur_g and (slots[cur_g[0]][4] != slot[4] or cur_cols + n_recv > max(1, group_sets)):
             groups.append(cur_g)
             cur_g, cur_cols = [], 0
         cur_g.append(idx)
@@ -229,8 +225,6 @@ def ring_all_vs_all(eng, n_genomes: int, world: int, rank: int, device, panel_ge
 
     if groups:
         post_group(groups[0])
-        if len(groups) > 1:
-            post_group(groups[1])  # the first group is small: keep the link busy behind it
 
     # diagonal block: my genomes against each other (runs while the first group is in flight)
     if m >= 2:
@@ -241,7 +235,7 @@ def ring_all_vs_all(eng, n_genomes: int, world: int, rank: int, device, panel_ge
         emit(a.astype(np.int64) + base, b.astype(np.int64) + base, inter, d)
 
     for gi_, g in enumerate(groups):
-        if gi_ >= 1 and gi_ + 1 < len(groups):  # (group 1 was posted together with group 0)
+        if gi_ + 1 < len(groups):
             post_group(groups[gi_ + 1])  # in flight while this group is intersected
         rows = slots[g[0]][4]
         parts, bufs, cols = [], [], []
