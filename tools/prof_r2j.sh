@@ -4,9 +4,10 @@
 #   3. ncu launch list of one config-2 step   4. ncu --set full of k_join on the same step
 mkdir -p gpurun_out
 timeout 1800 python -m pytest tests -m gpu -q > gpurun_out/r2j_tests.log 2>&1; echo "pytest rc=$?" | tee -a gpurun_out/r2j_tests.log
+python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/r2j_smoke.log 2>&1; echo "smoke rc=$?"
 tail -3 gpurun_out/r2j_tests.log
 timeout 900 python bench.py > gpurun_out/r2j_bench_n1.json 2> gpurun_out/r2j_bench_n1.err; echo "bench rc=$?"
-timeout 900 python bench.py --impl reference --steps 1 --warmup 0 > gpurun_out/r2j_bench_ref.json 2> gpurun_out/r2j_bench_ref.err; echo "ref rc=$?"
+if [ "${REF:-0}" = "1" ]; then timeout 900 python bench.py --impl reference --steps 1 --warmup 0 > gpurun_out/r2j_bench_ref.json 2> gpurun_out/r2j_bench_ref.err; echo "ref rc=$?"; fi
 CMD="python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-e2e"
 timeout 300 $CMD > gpurun_out/r2j_plain.log 2>&1 && \
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 6000 --csv --log-file gpurun_out/r2j_launches.csv $CMD > gpurun_out/r2j_ncu_list.log 2>&1
