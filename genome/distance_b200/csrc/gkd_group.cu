@@ -181,26 +181,51 @@ void member_ring(gkd_group *g, uint32_t x, uint64_t *inter, double *dist) {
         if (row1 <= row0) continue;
         for (auto &p : plan_panels(g->members[src].arenas, rc0, rc1, g->panel_sets)) slots.push_back(Slot{std::move(p), src, row0, row1});
     }
-    auto post = [&](size_t k) {  // start the peer copy of slot k into receive buffer k & 1
-        const Slot &S = slots[k];
-        const int b = (int)(k & 1);
-        const uint64_t bytes = S.p.end - S.p.begin;
-        if (bytes > M.recv_cap[b]) {
+    // Panels are the unit of transfer; the unit of compute is a GROUP of consecutive panels that meet the same rows, up
+    // to GROUP_SETS sets (possibly of several peers): kernel 4's block join builds one table per (64 rows, key range) and
+    // probes every column of the call with it, so one call over many columns amortises the tables.
+    constexpr uint32_t GROUP_SETS = 1024;
+    struct Group {
+        size_t s0, s1;  // slots [s0, s1)
+        std::vector<uint64_t> off;  // byte offset of every panel in the receive buffer
+        uint64_t bytes;
+    };
+    std::vector<Group> groups;
+    for (size_t k = 0; k < slots.size();) {
+        Group G{k, k, {}, 0};
+        uint32_t sets = 0;
+        while (G.s1 < slots.size() && slots[G.s1].row0 == slots[k].row0 && slots[G.s1].row1 == slots[k].row1 &&
+               (G.s1 == k || sets + slots[G.s1].p.count <= GROUP_SETS)) {
+            G.off.push_back(G.bytes);
+            G.bytes += (slots[G.s1].p.end - slots[G.s1].p.begin + 255) & ~255ull;
+            sets += slots[G.s1].p.count;
+            G.s1++;
+        }
+        groups.push_back(std::move(G));
+        k = groups.back().s1;
+    }
+    auto post = [&](size_t gi) {  // start the peer copies of group gi into receive buffer gi & 1
+        const Group &G = groups[gi];
+        const int b = (int)(gi & 1);
+        if (G.bytes > M.recv_cap[b]) {
             if (M.recv[b]) MCK(cudaFree(M.recv[b]));
             M.recv[b] = nullptr;
             M.recv_cap[b] = 0;
-            MCK(cudaMalloc(&M.recv[b], bytes + bytes / 8 + 256));
-            M.recv_cap[b] = bytes + bytes / 8 + 256;
+            MCK(cudaMalloc(&M.recv[b], G.bytes + G.bytes / 8 + 256));
+            M.recv_cap[b] = G.bytes + G.bytes / 8 + 256;
         }
-        const Member &O = g->members[S.src];
-        const char *src_ptr = O.arenas[S.p.arena].base + S.p.begin;
-        MCK(cudaMemcpyPeerAsync(M.recv[b], M.device, src_ptr, O.device, bytes, M.copy_stream));
+        for (size_t k = G.s0; k < G.s1; k++) {
+            const Slot &S = slots[k];
+            const Member &O = g->members[S.src];
+            const char *src_ptr = O.arenas[S.p.arena].base + S.p.begin;
+            MCK(cudaMemcpyPeerAsync((char *)M.recv[b] + G.off[k - G.s0], M.device, src_ptr, O.device, S.p.end - S.p.begin, M.copy_stream));
+        }
         MCK(cudaEventRecord(M.copy_done[b], M.copy_stream));
     };
-    if (!slots.empty()) post(0);
+    if (!groups.empty()) post(0);
     if (M.rc) return;
 
-    // diagonal block (runs while the first panel is in flight)
+    // diagonal block (runs while the first group is in flight)
     if (m >= 2) {
         const uint64_t cnt = (uint64_t)m * (m - 1) / 2;
         bi.resize(cnt);
@@ -211,28 +236,39 @@ void member_ring(gkd_group *g, uint32_t x, uint64_t *inter, double *dist) {
             for (uint32_t j = i + 1; j < m; j++, t++) put(M.global_ids[i], M.global_ids[j], bi[t], bd[t]);
     }
     std::vector<uint32_t> rows, cols;
-    for (size_t k = 0; k < slots.size(); k++) {
-        if (k + 1 < slots.size()) {
-            // buffer (k+1)&1 was last used by slot k-1, whose sets were dropped (and the stream drained) below
-            post(k + 1);
+    for (size_t gi = 0; gi < groups.size(); gi++) {
+        if (gi + 1 < groups.size()) {
+            // buffer (gi+1)&1 was last used by group gi-1, whose sets were dropped (and the stream drained) below
+            post(gi + 1);
             if (M.rc) return;
         }
-        const Slot &S = slots[k];
-        const int b = (int)(k & 1);
+        const Group &G = groups[gi];
+        const int b = (int)(gi & 1);
         MCK(cudaEventSynchronize(M.copy_done[b]));
-        uint32_t first = 0;
-        MGK(gkd_adopt_sets(M.ctx, M.recv[b], S.p.end - S.p.begin, S.p.table.data(), S.p.count, &first));
+        const Slot &S0 = slots[G.s0];
         rows.clear();
         cols.clear();
-        for (uint32_t r = S.row0; r < S.row1; r++) rows.push_back(r);
-        for (uint32_t c = 0; c < S.p.count; c++) cols.push_back(first + c);
+        for (uint32_t r = S0.row0; r < S0.row1; r++) rows.push_back(r);
+        for (size_t k = G.s0; k < G.s1; k++) {
+            const Slot &S = slots[k];
+            uint32_t first = 0;
+            MGK(gkd_adopt_sets(M.ctx, (char *)M.recv[b] + G.off[k - G.s0], S.p.end - S.p.begin, S.p.table.data(), S.p.count, &first));
+            for (uint32_t c = 0; c < S.p.count; c++) cols.push_back(first + c);
+        }
         bi.resize((size_t)rows.size() * cols.size());
         bd.resize(bi.size());
         MGK(gkd_query_vs_ref(M.ctx, rows.data(), (uint32_t)rows.size(), cols.data(), (uint32_t)cols.size(), bi.data(), bd.data()));
-        const std::vector<uint32_t> &their = g->members[S.src].global_ids;
-        size_t t = 0;
-        for (uint32_t r = S.row0; r < S.row1; r++)
-            for (uint32_t c = 0; c < S.p.count; c++, t++) put(M.global_ids[r], their[S.p.first + c], bi[t], bd[t]);
+        size_t col0 = 0;
+        for (size_t k = G.s0; k < G.s1; k++) {
+            const Slot &S = slots[k];
+            const std::vector<uint32_t> &their = g->members[S.src].global_ids;
+            for (uint32_t r = S0.row0; r < S0.row1; r++)
+                for (uint32_t c = 0; c < S.p.count; c++) {
+                    const size_t t = (size_t)(r - S0.row0) * cols.size() + col0 + c;
+                    put(M.global_ids[r], their[S.p.first + c], bi[t], bd[t]);
+                }
+            col0 += S.p.count;
+        }
         MGK(gkd_truncate(M.ctx, m));
     }
 }
