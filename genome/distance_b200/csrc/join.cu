@@ -241,11 +241,17 @@ __global__ void __launch_bounds__(THREADS, CTAS)
         uint32_t G = (ncols + 31u) / 32u;
         if (G < 3u * NW) G = 3u * NW;
         if (G > ncols) G = ncols;
-        uint32_t my_rowid[RW], my_rowpos[RW];
+        // lane r answers for row 32w + r in the validity ballots; the tally reduction (flush, below) leaves lane l with
+        // the counts of the rows frow(l, 0..RW-1), so those are the ids it needs for the result slots
+        uint32_t my_rowid[RW], f_rowid[RW], f_rowpos[RW];
 #pragma unroll
         for (int w = 0; w < RW; w++) {
             my_rowid[w] = ti.rowid[w * 32 + lane];
-            my_rowpos[w] = ti.rowpos[w * 32 + lane];
+            uint32_t fr;
+            if (RW == 2) fr = 32u * ((lane >> 4) & 1u) + (((lane >> 3) & 1u) << 2 | ((lane >> 2) & 1u) << 1 | ((lane >> 1) & 1u)) + 8u * (2u * (lane & 1u) + (uint32_t)w);
+            else fr = (((lane >> 4) & 1u) << 2 | ((lane >> 3) & 1u) << 1 | ((lane >> 2) & 1u)) + 8u * (2u * ((lane >> 1) & 1u) + (lane & 1u));
+            f_rowid[w] = ti.rowid[fr];
+            f_rowpos[w] = ti.rowpos[fr];
         }
         for (;;) {
             uint32_t g = 0;
@@ -297,23 +303,53 @@ __global__ void __launch_bounds__(THREADS, CTAS)
                 for (int w = 0; w < RW; w++)
                     rowmask[w] = plan.mode == PAIRS_UPPER ? __ballot_sync(FULL, my_rowid[w] < cid) : FULL;
                 uint32_t pending = 0;  // trips added to acc since the last flush (warp-uniform)
-                uint32_t cnt[RW];      // lane r: matches of rows r (, r + 32) with this column in this range
+                uint32_t cnt[RW];      // lane l: matches of its rows frow(l, .) with this column in this range
 #pragma unroll
                 for (int w = 0; w < RW; w++) cnt[w] = 0;
+                // Sum of every byte counter over the 32 lanes, as a reduce-scatter on the packed words: each step a lane
+                // keeps half of its words (later: half of its bytes) and receives the partner's copy of that half, so
+                // after five steps lane l holds the totals of its RW rows frow(l, .).  Per-lane counters stay <= 7
+                // (PEND_MAX trips), so no byte exceeds 32 * 7 on the way.
                 auto flush = [&]() {
+                    constexpr int NREG = 8 * RW;
+                    uint32_t r[NREG];
 #pragma unroll
-                    for (int w = 0; w < RW; w++) {
+                    for (int w = 0; w < RW; w++)
 #pragma unroll
                         for (int x = 0; x < 8; x++) {
-                            const uint32_t even = __reduce_add_sync(FULL, acc[w][x] & 0x00FF00FFu);        // rows x, x+16
-                            const uint32_t odd = __reduce_add_sync(FULL, (acc[w][x] >> 8) & 0x00FF00FFu);  // rows x+8, x+24
-                            const uint32_t v = (lane & 8u) ? odd : even;
-                            if ((lane & 7u) == (uint32_t)x) cnt[w] += (lane & 16u) ? (v >> 16) : (v & 0xFFFFu);
+                            r[w * 8 + x] = acc[w][x];
                             acc[w][x] = 0;
                         }
+                    uint32_t bit = 16u;
+#pragma unroll
+                    for (int n = NREG; n > 1; n >>= 1, bit >>= 1) {
+                        const bool up = (lane & bit) != 0u;
+#pragma unroll
+                        for (int y = 0; y < n / 2; y++) {
+                            const uint32_t send = up ? r[y] : r[y + n / 2];
+                            const uint32_t keep = up ? r[y + n / 2] : r[y];
+                            r[y] = keep + __shfl_xor_sync(FULL, send, bit);
+                        }
+                    }
+                    uint32_t v = r[0];
+                    if (RW == 1) {  // bit == 2: keep two of the four bytes
+                        const bool up = (lane & 2u) != 0u;
+                        const uint32_t send = up ? (v & 0xFFFFu) : (v >> 16), keep = up ? (v >> 16) : (v & 0xFFFFu);
+                        v = keep + __shfl_xor_sync(FULL, send, 2);
+                        const bool up1 = (lane & 1u) != 0u;
+                        const uint32_t send1 = up1 ? (v & 0xFFu) : ((v >> 8) & 0xFFu), keep1 = up1 ? ((v >> 8) & 0xFFu) : (v & 0xFFu);
+                        cnt[0] += keep1 + __shfl_xor_sync(FULL, send1, 1);
+                    } else {  // bit == 1: keep two of the four bytes, one per mask word position
+                        const bool up = (lane & 1u) != 0u;
+                        const uint32_t send = up ? (v & 0xFFFFu) : (v >> 16), keep = up ? (v >> 16) : (v & 0xFFFFu);
+                        v = keep + __shfl_xor_sync(FULL, send, 1);
+                        cnt[0] += v & 0xFFu;
+                        cnt[RW - 1] += (v >> 8) & 0xFFu;
                     }
                     pending = 0;
                 };
+                constexpr uint32_t PEND_MAX = 7 / KPT > 0 ? 7 / KPT : 1;
+                static_assert(KPT <= 7, "byte counters: a lane adds at most 7 per flush");
                 for (uint32_t base = lo; base < hi; base += 32u * KPT) {
                     uint32_t m[RW][KPT], anym = 0;
 #pragma unroll
@@ -345,21 +381,22 @@ __global__ void __launch_bounds__(THREADS, CTAS)
                             for (int q = 0; q < KPT; q++)
 #pragma unroll
                                 for (int x = 0; x < 8; x++) acc[w][x] += (m[w][q] >> x) & 0x01010101u;
-                        if (++pending == 255u / KPT) flush();  // before a byte counter can overflow
+                        pending++;
                     }
+                    // one call site: when the counters are due, or behind the column's last trip
+                    if (pending && (pending == PEND_MAX || base + 32u * KPT >= hi)) flush();
                 }
-                if (pending) flush();
 #pragma unroll
                 for (int w = 0; w < RW; w++) {
                     if (!cnt[w]) continue;
                     unsigned long long t;
                     bool valid = true;
                     if (plan.mode == PAIRS_UPPER) {
-                        const unsigned long long i = my_rowid[w], n = plan.n_cols;
+                        const unsigned long long i = f_rowid[w], n = plan.n_cols;
                         t = i * (2ull * n - i - 1ull) / 2ull + ((unsigned long long)cid - i - 1ull) - plan.first;
                         valid = t < plan.count;  // pairs before `first` wrap around to huge values
                     } else {
-                        t = (unsigned long long)my_rowpos[w] * plan.stride_r +
+                        t = (unsigned long long)f_rowpos[w] * plan.stride_r +
                             (unsigned long long)(cbeg + g + j * G) * plan.stride_c;
                     }
                     if (valid) atomicAdd(&counts[t], cnt[w]);
