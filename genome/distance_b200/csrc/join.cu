@@ -1,4 +1,4 @@
-// join.cu -- kernel 4, block-join form: 32 row sets against every column set at once.
+// join.cu -- kernel 4, block-join form: a block of 64 (or 32) row sets against every column set at once.
 //
 // Reference semantics restated (same as intersect.cu): SequenceKmers.similarity = number of members of one
 // HashSet<String> found in the other, for every pair the caller enumerates -- the strict upper triangle of
@@ -6,27 +6,28 @@
 // The reference probes one hash set with the members of the other, pair by pair.  The bucket-merge kernel
 // (intersect.cu) streams both sets of every pair; for a pair MATRIX that repeats the same work row after row:
 // a column key is compared with every row separately.  This kernel keeps the reference's probe formulation but
-// shares the probe between 32 rows:
+// shares the probe between the rows of a block:
 //
-//   * the key space is cut into 2^L equal ranges (L per class of row sizes, chosen so that the keys 32 rows
-//     hold in one range fill ~30 % of the table).  Sets are stored in mixed-key order with bucket offset
+//   * the key space is cut into 2^L equal ranges (L per class of row sizes, chosen so that the keys a block of
+//     rows holds in one range fill ~30 % of the table).  Sets are stored in mixed-key order with bucket offset
 //     tables (gkd_internal.cuh), so the keys any set holds in a range are one contiguous run of its low words;
-//   * a task = (block of 32 rows, range).  The CTA builds ONE open-addressing table in shared memory:
-//     key (32-bit low word; the range pins the other bits) -> 32-bit mask of the rows that hold it
-//     (find-or-insert with atomicCAS on the key word, atomicOr on the mask word: lock-free, no ordering
-//     between rows needed);
-//   * then every column set's run of the same range is streamed once from L2/HBM (coalesced, 4 keys per lane
-//     in flight) and probed; a hit returns the row mask.  Misses -- nearly every probe of an unrelated
-//     genome -- cost one shared-memory load for 32 pairs at once;
-//   * hits are tallied per row with ballots (lane r keeps the count of row r) and flushed with one
-//     atomicAdd per (row, column, range) that saw a match.
+//   * a task = (row block, range).  The CTA builds ONE open-addressing table in shared memory: key (32-bit low
+//     word -- the range pins the other bits -- or the whole 64-bit h of wide keys) -> one 32-bit mask word per 32
+//     rows naming the rows that hold it (find-or-insert with atomicCAS on the key word, atomicOr on the mask word:
+//     lock-free, no ordering between rows needed; the runs' total is checked first, so the table cannot fill up);
+//   * then every column set's run of the same range is streamed once from L2/HBM (coalesced, KPT keys per lane,
+//     the next column's keys requested before the current one is probed) and probed; a hit returns the row mask.
+//     Misses -- nearly every probe of an unrelated genome -- settle all rows of the block at once;
+//   * hits are tallied in packed byte counters per lane, summed over the warp with a reduce-scatter on the packed
+//     words for columns that had a match, and flushed with one atomicAdd per (row, column, range) that saw one;
+//   * warp 0 looks up the next task (rows, runs) while the other warps still probe the current table.
 //
-// Per pair and column key this is 1/32 (1/64 with 64-row blocks: two mask words per slot) of a probe instead of
-// a two-pointer merge step, and every set is read once per ROW BLOCK instead of once per row; tasks are enumerated range-major so the column runs of one range
-// are served from L2 to all row blocks.  Counts are exact (a key's identity inside a range is its low word).
-// Serves 32-bit low words (DNA/RNA K <= 21, protein K <= 5) and 64-bit keys (the table then holds the whole h) when a
-// call has enough rows and columns; everything else (lists, greedy pass, tiny sets, thin slices, palindrome sub-sets)
-// stays on the merge kernel.
+// Per pair and column key this is 1/64 (1/32) of a probe instead of a two-pointer merge step, and every set is read
+// once per ROW BLOCK instead of once per row; tasks are enumerated range-major so the column runs of one range are
+// served from L2 to all row blocks (HBM sees every set once per call).  Counts are exact (a key's identity inside a
+// range is its low word).  Serves 32-bit low words (DNA/RNA K <= 21, protein K <= 5) and 64-bit keys when a call has
+// enough rows and columns; everything else (lists, greedy pass, tiny sets, thin slices, palindrome sub-sets) stays on
+// the merge kernel.  DESIGN.md section 4 has the cost model and the measurements.
 #include <cstdlib>
 
 #include "gkd_internal.cuh"
